@@ -1,0 +1,152 @@
+/*
+ * ronk_b200.h — C ABI of libronk_b200.so: the B200-native (sm_100a) replacement for
+ * pluto/ronkathon's PrimeField / Polynomial / kzg::commit hot path.
+ *
+ * The reference is a pure-Rust crate with no FFI of its own; this header is the boundary a
+ * `ronkathon-b200-sys` crate would bind 1:1 (bindings/rust/).  Each entry
+ * point cites the reference item it replaces (file:line relative to the ronkathon tree).
+ *
+ * Conventions
+ *  - Field elements are canonical residues in uint64_t (the reference's `PrimeField<P>{value: usize}`,
+ *    src/algebra/field/prime/mod.rs:39-42).  Inputs must be canonical (< p); outputs always are.
+ *  - `p` is the modulus, `g` the multiplicative generator (FiniteField::PRIMITIVE_ELEMENT).
+ *    p = 0xFFFFFFFF00000001 (Goldilocks) takes the specialised kernels; any other odd prime
+ *    < 2^64 takes the generic Montgomery kernels (same code path the p = 101 / 17 / 127
+ *    cross-checks run through).  p = 2 is not supported (RONK_EUNSUPPORTED).
+ *  - Pointers without a `_host` suffix in the function name are DEVICE pointers on the context's
+ *    device; work is enqueued on the context's stream and is asynchronous unless stated.
+ *    `_host` variants take host pointers, copy in, run, copy out and synchronise.
+ *  - Every function returns 0 (RONK_OK) or an error code; nothing throws, aborts or falls back
+ *    to a CPU path.  Where the reference would panic/assert, RONK_EINVAL is returned.
+ *  - Curve points (AffinePoint<PlutoExtendedCurve>, src/curve/mod.rs:67-74) are 4 bytes
+ *    x0,x1,y0,y1 with x = x0 + x1·t in GF(101²) = F101[t]/(t²+2); 0xFF,0xFF,0xFF,0xFF = Infinity.
+ *    Scalars (PlutoScalarField = F17) are one byte each, < 17.
+ *  - The caller owns every buffer; the library never retains caller pointers past stream order.
+ */
+#ifndef RONK_B200_H
+#define RONK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RONK_OK 0
+#define RONK_EINVAL 1       /* the reference would panic/assert on this input */
+#define RONK_ECUDA 2        /* CUDA runtime error (see ronk_last_error) */
+#define RONK_ENOMEM 3       /* device allocation failed */
+#define RONK_ENCCL 4        /* collective error */
+#define RONK_EUNSUPPORTED 5 /* outside the supported envelope (e.g. log_n too large) */
+
+#define RONK_GOLDILOCKS 0xFFFFFFFF00000001ULL
+
+typedef struct ronk_ctx ronk_ctx;
+
+/* ---- context ---------------------------------------------------------------------------- */
+/* Opaque context: device, stream, twiddle/plan cache, workspace.  `stream` is a cudaStream_t
+ * (NULL = the legacy default stream).  One context per host thread. */
+int ronk_ctx_create(ronk_ctx **out, int device, void *stream);
+int ronk_ctx_destroy(ronk_ctx *ctx);
+int ronk_ctx_set_stream(ronk_ctx *ctx, void *stream);
+int ronk_sync(ronk_ctx *ctx);
+const char *ronk_strerror(int code);
+const char *ronk_last_error(ronk_ctx *ctx);
+/* Number of kernels this context has launched (bench.py's `gpu_launches`). */
+uint64_t ronk_launch_count(ronk_ctx *ctx);
+/* Kernel profiling: when on, every kernel launch is bracketed by CUDA events on the context's
+ * stream.  ronk_prof_fetch synchronises, writes up to `max` (name, ms) records in launch order,
+ * returns the number written and clears the log. */
+int ronk_prof_enable(ronk_ctx *ctx, int on);
+int ronk_prof_fetch(ronk_ctx *ctx, char (*names)[32], float *ms, int max);
+/* Device memory helpers so a host-language binding needs no CUDA runtime of its own. */
+int ronk_dev_alloc(ronk_ctx *ctx, void **dptr, size_t bytes);
+int ronk_dev_free(ronk_ctx *ctx, void *dptr);
+int ronk_memcpy_h2d(ronk_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int ronk_memcpy_d2h(ronk_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+
+/* ---- FiniteField metadata (host side, O(log p)) ----------------------------------------- */
+/* FiniteField::PRIMITIVE_ELEMENT — src/algebra/field/prime/mod.rs:87-123.  Known moduli only:
+ * 101→2, 17→14, 127→3, 59→2 (the reference's own search results), Goldilocks→7. */
+int ronk_field_generator(uint64_t p, uint64_t *g);
+/* FiniteField::primitive_root_of_unity(n) — src/algebra/field/mod.rs:70-75.
+ * RONK_EINVAL when n does not divide p-1 (the reference's assert). */
+int ronk_root_of_unity(uint64_t p, uint64_t g, uint64_t n, uint64_t *out);
+
+/* ---- PrimeField<P> element-wise arithmetic on arrays ------------------------------------ */
+/* Add/Sub/Mul/Neg — src/algebra/field/prime/arithmetic.rs:6,22-27,37,64. out may alias a or b. */
+int ronk_field_add_u64(ronk_ctx *ctx, uint64_t p, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int ronk_field_sub_u64(ronk_ctx *ctx, uint64_t p, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int ronk_field_mul_u64(ronk_ctx *ctx, uint64_t p, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int ronk_field_neg_u64(ronk_ctx *ctx, uint64_t p, const uint64_t *a, uint64_t *out, size_t n);
+/* Field::pow(self, power) — src/algebra/field/prime/mod.rs:74-84 (same value, O(log e)). */
+int ronk_field_pow_u64(ronk_ctx *ctx, uint64_t p, const uint64_t *a, uint64_t e, uint64_t *out, size_t n);
+/* Field::inverse — src/algebra/field/prime/mod.rs:62-72 (a^(p-2)).  Synchronous: returns
+ * RONK_EINVAL if any input is 0 (the reference's None / unwrap panic); outputs for zeros are 0. */
+int ronk_field_inv_u64(ronk_ctx *ctx, uint64_t p, const uint64_t *a, uint64_t *out, size_t n);
+/* Div — src/algebra/field/prime/arithmetic.rs:54 (a * b^-1).  Synchronous; RONK_EINVAL on b=0. */
+int ronk_field_div_u64(ronk_ctx *ctx, uint64_t p, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+/* Host-pointer variants (op: 0 add, 1 sub, 2 mul, 3 div; unary: 0 neg, 1 inverse). */
+int ronk_field_binop_u64_host(ronk_ctx *ctx, int op, uint64_t p, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+int ronk_field_unop_u64_host(ronk_ctx *ctx, int op, uint64_t p, const uint64_t *a, uint64_t *out, size_t n);
+int ronk_field_pow_u64_host(ronk_ctx *ctx, uint64_t p, const uint64_t *a, uint64_t e, uint64_t *out, size_t n);
+
+/* ---- transforms -------------------------------------------------------------------------- */
+/* Polynomial::fft / ifft — src/polynomial/mod.rs:273-323 / :430-484.  In place, `batch`
+ * contiguous transforms of 2^log_n points, NATURAL order in and out, X[k] = Σ_j a_j ω^(jk),
+ * ω = g^((p-1)/2^log_n); inverse uses ω^-1 and scales by (2^log_n)^-1.
+ * RONK_EINVAL if 2^log_n does not divide p-1; RONK_EUNSUPPORTED if log_n > 24. */
+int ronk_ntt_u64(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *data, uint32_t log_n, uint32_t batch, int inverse);
+int ronk_ntt_u64_host(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *host_data, uint32_t log_n, uint32_t batch, int inverse);
+/* Forward transform whose last stage also multiplies point-wise by `mul` (same shape, natural
+ * order): data[k] = NTT(data)[k] * mul[k].  The fused form of the evaluate→multiply step. */
+int ronk_ntt_mul_u64(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *data, const uint64_t *mul, uint32_t log_n, uint32_t batch);
+/* Polynomial::dft — src/polynomial/mod.rs:240-258.  Any n | p-1 (O(n²)); out must not alias in. */
+int ronk_dft_u64(ronk_ctx *ctx, uint64_t p, uint64_t g, const uint64_t *in, uint64_t n, uint64_t *out);
+int ronk_dft_u64_host(ronk_ctx *ctx, uint64_t p, uint64_t g, const uint64_t *in, uint64_t n, uint64_t *out);
+
+/* ---- Polynomial<Monomial, F, D> ----------------------------------------------------------- */
+/* Mul — src/polynomial/arithmetic.rs:97-119.  c has da+db-1 coefficients (no trimming).
+ * NTT path (pad → NTT, NTT∘pointwise → iNTT) when a power of two ≥ da+db-1 divides p-1 and
+ * the product is large enough to pay for it, else the schoolbook kernel (e.g. p = 101). */
+int ronk_poly_mul_u64(ronk_ctx *ctx, uint64_t p, uint64_t g, const uint64_t *a, size_t da, const uint64_t *b, size_t db, uint64_t *c);
+int ronk_poly_mul_u64_host(ronk_ctx *ctx, uint64_t p, uint64_t g, const uint64_t *a, size_t da, const uint64_t *b, size_t db, uint64_t *c);
+/* Add/Sub/Neg — src/polynomial/arithmetic.rs:16-94: out has da terms, b zero-extended/truncated. */
+int ronk_poly_add_u64(ronk_ctx *ctx, uint64_t p, const uint64_t *a, size_t da, const uint64_t *b, size_t db, uint64_t *out);
+int ronk_poly_sub_u64(ronk_ctx *ctx, uint64_t p, const uint64_t *a, size_t da, const uint64_t *b, size_t db, uint64_t *out);
+/* evaluate — src/polynomial/mod.rs:133-139: out[i] = Σ_j coeffs[j] * xs[i]^j for m points. */
+int ronk_poly_eval_u64(ronk_ctx *ctx, uint64_t p, const uint64_t *coeffs, size_t d, const uint64_t *xs, size_t m, uint64_t *out);
+int ronk_poly_eval_u64_host(ronk_ctx *ctx, uint64_t p, const uint64_t *coeffs, size_t d, const uint64_t *xs, size_t m, uint64_t *out);
+/* Lagrange-basis evaluate — src/polynomial/mod.rs:382-415 (nodes ω_n^i, barycentric; returns the
+ * coefficient itself when x is a node).  Host pointers, n | p-1. */
+int ronk_poly_lagrange_eval_u64_host(ronk_ctx *ctx, uint64_t p, uint64_t g, const uint64_t *coeffs, size_t n, uint64_t x, uint64_t *out);
+/* quotient_and_remainder / Div / Rem — src/polynomial/mod.rs:170-225, arithmetic.rs:121-146.
+ * q and r both have da terms.  Host pointers.  RONK_EINVAL for an all-zero divisor. */
+int ronk_poly_divrem_u64_host(ronk_ctx *ctx, uint64_t p, const uint64_t *a, size_t da, const uint64_t *b, size_t db, uint64_t *q, uint64_t *r);
+
+/* ---- curve + kzg::commit ------------------------------------------------------------------ */
+/* AffinePoint Add / Neg / Mul<ScalarField> — src/curve/mod.rs:178-213, :225-235, :157-172,
+ * element-wise over n points (host pointers).  RONK_EINVAL for off-curve / malformed input. */
+int ronk_point_add_pluto_ext_host(ronk_ctx *ctx, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
+int ronk_point_neg_pluto_ext_host(ronk_ctx *ctx, const uint8_t *a, uint8_t *out, size_t n);
+int ronk_point_smul_pluto_ext_host(ronk_ctx *ctx, const uint8_t *a, const uint8_t *scalars, uint8_t *out, size_t n);
+/* kzg::commit — src/kzg/setup.rs:48-60: Σ points[i]·scalars[i] for i < n_scalars as a Pippenger
+ * bucket MSM.  RONK_EINVAL if n_points < n_scalars (the reference's assert), if a scalar ≥ 17
+ * or if a point is off-curve.  `points`/`scalars` are device pointers, `out` is a 4-byte HOST
+ * buffer; synchronous. */
+int ronk_msm_pluto_ext(ronk_ctx *ctx, const uint8_t *points, size_t n_points, const uint8_t *scalars, size_t n_scalars, uint8_t out[4]);
+int ronk_msm_pluto_ext_host(ronk_ctx *ctx, const uint8_t *points, size_t n_points, const uint8_t *scalars, size_t n_scalars, uint8_t out[4]);
+/* Per-device partial MSM for the multi-GPU path: writes the 17 bucket sums (17×4 bytes, host)
+ * so ranks can combine them; ronk_msm_combine_buckets folds world×17 buckets into one point. */
+int ronk_msm_pluto_ext_buckets(ronk_ctx *ctx, const uint8_t *points, size_t n_points, const uint8_t *scalars, size_t n_scalars, uint8_t buckets[68]);
+int ronk_msm_combine_buckets_host(ronk_ctx *ctx, const uint8_t *buckets, size_t n_sets, uint8_t out[4]);
+
+/* ---- synthetic inputs --------------------------------------------------------- */
+/* splitmix64 stream reduced mod p, generated on the device: out[i] = splitmix64(seed, i) % p. */
+int ronk_splitmix_fill_u64(ronk_ctx *ctx, uint64_t p, uint64_t seed, uint64_t *out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RONK_B200_H */

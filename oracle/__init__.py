@@ -55,6 +55,8 @@ def lib():
             "orc_lagrange_eval": (i32, [u64, u64, p64, u64, u64, p64]),
             "orc_ntt_fast": (i32, [u64, u64, p64, u64, i32]),
             "orc_splitmix_fill": (None, [u64, u64, p64, u64]),
+            "orc_vec_mul": (None, [u64, p64, p64, p64, u64]),
+            "orc_poly_eval_horner": (u64, [u64, p64, u64, u64]),
             "orc_gf_add": (None, [pu8, pu8, pu8]), "orc_gf_sub": (None, [pu8, pu8, pu8]),
             "orc_gf_neg": (None, [pu8, pu8]), "orc_gf_mul": (None, [pu8, pu8, pu8]),
             "orc_gf_inv": (i32, [pu8, pu8]),
@@ -134,6 +136,16 @@ def splitmix(p, seed, n) -> np.ndarray:
     out = np.empty(n, dtype=np.uint64)
     lib().orc_splitmix_fill(p, seed, _p64(out), n)
     return out
+
+
+def vec_mul(p, a, b):
+    a, b = _arr(a), _arr(b); out = np.empty(len(a), np.uint64)
+    lib().orc_vec_mul(p, _p64(a), _p64(b), _p64(out), len(a)); return out
+
+
+def poly_eval_horner(p, c, x):
+    c = _arr(c)
+    return lib().orc_poly_eval_horner(p, _p64(c), len(c), x % p)
 
 
 # ---- polynomial -----------------------------------------------------------------------------

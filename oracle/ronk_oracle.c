@@ -349,6 +349,18 @@ int orc_ntt_fast(u64 p, u64 g, u64 *a, u64 n, int inverse) {
   return ORC_OK;
 }
 
+/* out[i] = a[i]*b[i] (prime/arithmetic.rs:37 element-wise) — used to build the convolution-theorem check. */
+void orc_vec_mul(u64 p, const u64 *a, const u64 *b, u64 *out, u64 n) {
+  for (u64 i = 0; i < n; i++) out[i] = orc_mul(p, a[i], b[i]);
+}
+/* Horner evaluation: same value as orc_poly_eval (which is the reference's O(D²) form); used for
+ * spot checks X[k] == a(ω^k) at sizes where the literal form is too slow. */
+u64 orc_poly_eval_horner(u64 p, const u64 *c, u64 d, u64 x) {
+  u64 r = 0;
+  for (u64 i = d; i-- > 0;) r = orc_add(p, orc_mul(p, r, x), c[i]);
+  return r;
+}
+
 /* splitmix64 stream reduced mod p — SURVEY.md §8c/§8d synthetic-input definition. */
 void orc_splitmix_fill(u64 p, u64 seed, u64 *out, u64 n) {
   u64 s = seed;

@@ -1,0 +1,132 @@
+// api.cu — context management, profiling and memory helpers of the C ABI (include/ronk_b200.h).
+#include "ronk_internal.h"
+
+using namespace ronk;
+
+extern "C" {
+
+const char* ronk_strerror(int code) {
+  switch (code) {
+    case RONK_OK: return "ok";
+    case RONK_EINVAL: return "invalid argument (the reference would panic here)";
+    case RONK_ECUDA: return "CUDA error";
+    case RONK_ENOMEM: return "out of device memory";
+    case RONK_ENCCL: return "collective error";
+    case RONK_EUNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error";
+  }
+}
+
+int ronk_ctx_create(ronk_ctx** out, int device, void* stream) {
+  if (!out) return RONK_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return RONK_ECUDA;  // no CPU fallback: fail loudly
+  if (device < 0 || device >= count) return RONK_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return RONK_ECUDA;
+  ronk_ctx* ctx = new ronk_ctx();
+  ctx->device = device;
+  ctx->stream = (cudaStream_t)stream;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return RONK_ECUDA; }
+  ctx->sm_count = prop.multiProcessorCount;
+  if (prop.major < 10) {  // sm_100a-only binary
+    delete ctx;
+    return RONK_EUNSUPPORTED;
+  }
+  if (cudaMalloc((void**)&ctx->d_flag, sizeof(int)) != cudaSuccess ||
+      cudaMallocHost((void**)&ctx->h_flag, sizeof(int)) != cudaSuccess) {
+    delete ctx;
+    return RONK_ENOMEM;
+  }
+  *out = ctx;
+  return RONK_OK;
+}
+
+int ronk_ctx_destroy(ronk_ctx* ctx) {
+  if (!ctx) return RONK_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->plans) {
+    NttPlan& p = kv.second;
+    if (p.tw1) cudaFree(p.tw1);
+    if (p.tw2) cudaFree(p.tw2);
+    if (p.tw_lo) cudaFree(p.tw_lo);
+    if (p.tw_hi_inv) cudaFree(p.tw_hi_inv);
+  }
+  for (auto& r : ctx->prof_log) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
+  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->ws2) cudaFree(ctx->ws2);
+  if (ctx->d_flag) cudaFree(ctx->d_flag);
+  if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+  delete ctx;
+  return RONK_OK;
+}
+
+int ronk_ctx_set_stream(ronk_ctx* ctx, void* stream) {
+  if (!ctx) return RONK_EINVAL;
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = (cudaStream_t)stream;
+  return RONK_OK;
+}
+
+int ronk_sync(ronk_ctx* ctx) {
+  if (!ctx) return RONK_EINVAL;
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RONK_OK;
+}
+
+const char* ronk_last_error(ronk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t ronk_launch_count(ronk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ronk_prof_enable(ronk_ctx* ctx, int on) {
+  if (!ctx) return RONK_EINVAL;
+  ctx->prof = on != 0;
+  return RONK_OK;
+}
+
+int ronk_prof_fetch(ronk_ctx* ctx, char (*names)[32], float* ms, int max) {
+  if (!ctx) return 0;
+  cudaStreamSynchronize(ctx->stream);
+  int n = 0;
+  for (auto& r : ctx->prof_log) {
+    if (n < max) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, r.start, r.stop);
+      if (names) std::memcpy(names[n], r.name, 32);
+      if (ms) ms[n] = t;
+      n++;
+    }
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
+  ctx->prof_log.clear();
+  return n;
+}
+
+int ronk_dev_alloc(ronk_ctx* ctx, void** dptr, size_t bytes) {
+  if (!ctx || !dptr) return RONK_EINVAL;
+  RONK_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
+  return RONK_OK;
+}
+int ronk_dev_free(ronk_ctx* ctx, void* dptr) {
+  if (!ctx) return RONK_EINVAL;
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  RONK_CUDA(ctx, cudaFree(dptr));
+  return RONK_OK;
+}
+int ronk_memcpy_h2d(ronk_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  if (!ctx) return RONK_EINVAL;
+  RONK_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RONK_OK;
+}
+int ronk_memcpy_d2h(ronk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  if (!ctx) return RONK_EINVAL;
+  RONK_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RONK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,280 @@
+// field_ops.cu — PrimeField<P> element-wise kernels and FiniteField metadata.
+// Mirrors src/algebra/field/prime/arithmetic.rs:3-71 and src/algebra/field/prime/mod.rs:58-123.
+#include "ronk_internal.h"
+
+namespace ronk {
+
+enum { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_DIV = 3 };
+enum { UOP_NEG = 0, UOP_INV = 1 };
+
+template <class F, int OP>
+__global__ void binop_kernel(const F f, const u64* a, const u64* b, u64* out,
+                             size_t n, int* flag) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 x = a[i], y = b[i];
+    u64 r;
+    if (OP == OP_ADD) r = f.add(x, y);
+    else if (OP == OP_SUB) r = f.sub(x, y);
+    else if (OP == OP_MUL) r = f.mul(x, y);
+    else {
+      if (y == 0) { atomicExch(flag, 1); r = 0; }                 // rhs.inverse().unwrap() panics
+      else r = f.mul(x, field_pow(f, y, f.modulus() - 2));        // prime/arithmetic.rs:54
+    }
+    out[i] = r;
+  }
+}
+
+template <class F, int OP>
+__global__ void unop_kernel(const F f, const u64* a, u64* out, size_t n, u64 e, int* flag) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 x = a[i];
+    u64 r;
+    if (OP == UOP_NEG) r = f.neg(x);
+    else if (OP == UOP_INV) {
+      if (x == 0) { atomicExch(flag, 1); r = 0; }                 // inverse() == None
+      else r = field_pow(f, x, f.modulus() - 2);                  // prime/mod.rs:62-72
+    } else r = field_pow(f, x, e);                                // prime/mod.rs:74-84
+    out[i] = r;
+  }
+}
+
+__global__ void splitmix_kernel(u64 p, u64 seed, u64* out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    u64 z = seed + (u64)(i + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    out[i] = z % p;
+  }
+}
+
+static bool h_is_prime(u64 n) {  // deterministic Miller–Rabin for 64-bit n
+  if (n < 2) return false;
+  for (u64 q : {2ULL, 3ULL, 5ULL, 7ULL, 11ULL, 13ULL, 17ULL, 19ULL, 23ULL, 29ULL, 31ULL, 37ULL}) {
+    if (n % q == 0) return n == q;
+  }
+  u64 d = n - 1;
+  int s = 0;
+  while ((d & 1) == 0) { d >>= 1; s++; }
+  for (u64 a : {2ULL, 3ULL, 5ULL, 7ULL, 11ULL, 13ULL, 17ULL, 19ULL, 23ULL, 29ULL, 31ULL, 37ULL}) {
+    u64 x = h_powmod(a, d, n);
+    if (x == 1 || x == n - 1) continue;
+    bool comp = true;
+    for (int r = 1; r < s; r++) {
+      x = h_mulmod(x, x, n);
+      if (x == n - 1) { comp = false; break; }
+    }
+    if (comp) return false;
+  }
+  return true;
+}
+
+// PrimeField::new's const is_prime(P) (prime/mod.rs:48-50, :92-100) panics for composite P.
+int validate_modulus(ronk_ctx* ctx, u64 p) {
+  if (p == GL_P) return RONK_OK;
+  if (p == 2) return set_err(ctx, RONK_EUNSUPPORTED, "p = 2 (AESField) is outside this library's scope");
+  if (!h_is_prime(p)) return set_err(ctx, RONK_EINVAL, "input is not a prime number");
+  return RONK_OK;
+}
+
+static int grid_for(ronk_ctx* ctx, size_t n, int threads) {
+  size_t blocks = (n + threads - 1) / threads;
+  size_t cap = (size_t)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  return (int)blocks;
+}
+
+static int reset_flag(ronk_ctx* ctx) {
+  RONK_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+  return RONK_OK;
+}
+static int read_flag(ronk_ctx* ctx, int* v) {
+  RONK_CUDA(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *v = *ctx->h_flag;
+  return RONK_OK;
+}
+
+template <int OP>
+static int binop(ronk_ctx* ctx, u64 p, const u64* a, const u64* b, u64* out, size_t n, const char* name) {
+  if (!ctx || (n && (!a || !b || !out))) return set_err(ctx, RONK_EINVAL, "null argument");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (n == 0) return RONK_OK;
+  if (OP == OP_DIV) RONK_TRY(reset_flag(ctx));
+  const int threads = 256, blocks = grid_for(ctx, n, threads);
+  if (p == GL_P) {
+    GoldilocksField f;
+    LaunchScope ls(ctx, name);
+    binop_kernel<GoldilocksField, OP><<<blocks, threads, 0, ctx->stream>>>(f, a, b, out, n, ctx->d_flag);
+  } else {
+    MontField f;
+    RONK_TRY(make_mont_field(ctx, p, 0, false, &f));
+    LaunchScope ls(ctx, name);
+    binop_kernel<MontField, OP><<<blocks, threads, 0, ctx->stream>>>(f, a, b, out, n, ctx->d_flag);
+  }
+  RONK_TRY(check_launch(ctx, name));
+  if (OP == OP_DIV) {
+    int v = 0;
+    RONK_TRY(read_flag(ctx, &v));
+    if (v) return set_err(ctx, RONK_EINVAL, "division by zero (inverse of 0 is None)");
+  }
+  return RONK_OK;
+}
+
+template <int OP>
+static int unop(ronk_ctx* ctx, u64 p, const u64* a, u64* out, size_t n, u64 e, const char* name) {
+  if (!ctx || (n && (!a || !out))) return set_err(ctx, RONK_EINVAL, "null argument");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (n == 0) return RONK_OK;
+  if (OP == UOP_INV) RONK_TRY(reset_flag(ctx));
+  const int threads = 256, blocks = grid_for(ctx, n, threads);
+  if (p == GL_P) {
+    GoldilocksField f;
+    LaunchScope ls(ctx, name);
+    unop_kernel<GoldilocksField, OP><<<blocks, threads, 0, ctx->stream>>>(f, a, out, n, e, ctx->d_flag);
+  } else {
+    MontField f;
+    RONK_TRY(make_mont_field(ctx, p, 0, false, &f));
+    LaunchScope ls(ctx, name);
+    unop_kernel<MontField, OP><<<blocks, threads, 0, ctx->stream>>>(f, a, out, n, e, ctx->d_flag);
+  }
+  RONK_TRY(check_launch(ctx, name));
+  if (OP == UOP_INV) {
+    int v = 0;
+    RONK_TRY(read_flag(ctx, &v));
+    if (v) return set_err(ctx, RONK_EINVAL, "inverse of 0 is None");
+  }
+  return RONK_OK;
+}
+
+}  // namespace ronk
+
+using namespace ronk;
+
+extern "C" {
+
+int ronk_field_generator(uint64_t p, uint64_t* g) {
+  if (!g) return RONK_EINVAL;
+  switch (p) {  // results of find_primitive_element (prime/mod.rs:110-123) for the reference's moduli
+    case 101: *g = 2; return RONK_OK;
+    case 17: *g = 14; return RONK_OK;
+    case 127: *g = 3; return RONK_OK;
+    case 59: *g = 2; return RONK_OK;
+    case RONK_GOLDILOCKS: *g = 7; return RONK_OK;  // pinned
+    default: break;
+  }
+  if (p < 3 || !h_is_prime(p)) return RONK_EINVAL;
+  if (p > (1ULL << 32)) return RONK_EUNSUPPORTED;  // pass g explicitly for other large moduli
+  // the reference's literal search, for other small primes
+  for (u64 i = 2; i * i <= p; i++) {
+    if ((p - 1) % i == 0) {
+      if (h_powmod(i, (p - 1) / i, p) != 1) { *g = i; return RONK_OK; }
+      else if (h_powmod(p + 1 - i, i, p) != 1) { *g = p + 1 - i; return RONK_OK; }
+    }
+  }
+  return RONK_EINVAL;  // panic!("generator not found")
+}
+
+int ronk_root_of_unity(uint64_t p, uint64_t g, uint64_t n, uint64_t* out) {
+  if (!out || p < 3 || g == 0 || g >= p) return RONK_EINVAL;
+  if (n == 0 || (p - 1) % n != 0) return RONK_EINVAL;  // assert!(p_minus_one % n == 0)
+  *out = h_powmod(g, (p - 1) / n, p);
+  return RONK_OK;
+}
+
+int ronk_field_add_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  return binop<OP_ADD>(ctx, p, (const u64*)a, (const u64*)b, (u64*)out, n, "field_add");
+}
+int ronk_field_sub_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  return binop<OP_SUB>(ctx, p, (const u64*)a, (const u64*)b, (u64*)out, n, "field_sub");
+}
+int ronk_field_mul_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  return binop<OP_MUL>(ctx, p, (const u64*)a, (const u64*)b, (u64*)out, n, "field_mul");
+}
+int ronk_field_div_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  return binop<OP_DIV>(ctx, p, (const u64*)a, (const u64*)b, (u64*)out, n, "field_div");
+}
+int ronk_field_neg_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, uint64_t* out, size_t n) {
+  return unop<UOP_NEG>(ctx, p, (const u64*)a, (u64*)out, n, 0, "field_neg");
+}
+int ronk_field_inv_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, uint64_t* out, size_t n) {
+  return unop<UOP_INV>(ctx, p, (const u64*)a, (u64*)out, n, 0, "field_inv");
+}
+int ronk_field_pow_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, uint64_t e, uint64_t* out, size_t n) {
+  return unop<2>(ctx, p, (const u64*)a, (u64*)out, n, e, "field_pow");
+}
+
+int ronk_splitmix_fill_u64(ronk_ctx* ctx, uint64_t p, uint64_t seed, uint64_t* out, size_t n) {
+  if (!ctx || (n && !out) || p == 0) return set_err(ctx, RONK_EINVAL, "bad argument");
+  if (n == 0) return RONK_OK;
+  {
+    LaunchScope ls(ctx, "splitmix_fill");
+    splitmix_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(p, seed, (u64*)out, n);
+  }
+  return check_launch(ctx, "splitmix_kernel");
+}
+
+// ---- host-pointer variants -------------------------------------------------------------------
+static int host_stage(ronk_ctx* ctx, size_t n, u64** da, u64** db, u64** dout) {
+  const size_t bytes = n * sizeof(u64);
+  RONK_TRY(ensure_ws(ctx, &ctx->ws2, &ctx->ws2_bytes, 3 * bytes));
+  *da = (u64*)ctx->ws2;
+  *db = *da + n;
+  *dout = *db + n;
+  return RONK_OK;
+}
+
+int ronk_field_binop_u64_host(ronk_ctx* ctx, int op, uint64_t p, const uint64_t* a, const uint64_t* b, uint64_t* out,
+                              size_t n) {
+  if (!ctx || (n && (!a || !b || !out))) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (n == 0) return RONK_OK;
+  u64 *da, *db, *dout;
+  RONK_TRY(host_stage(ctx, n, &da, &db, &dout));
+  RONK_CUDA(ctx, cudaMemcpyAsync(da, a, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  RONK_CUDA(ctx, cudaMemcpyAsync(db, b, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int rc;
+  switch (op) {
+    case 0: rc = ronk_field_add_u64(ctx, p, da, db, dout, n); break;
+    case 1: rc = ronk_field_sub_u64(ctx, p, da, db, dout, n); break;
+    case 2: rc = ronk_field_mul_u64(ctx, p, da, db, dout, n); break;
+    case 3: rc = ronk_field_div_u64(ctx, p, da, db, dout, n); break;
+    default: return set_err(ctx, RONK_EINVAL, "unknown op");
+  }
+  if (rc != RONK_OK) return rc;
+  RONK_CUDA(ctx, cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RONK_OK;
+}
+
+int ronk_field_unop_u64_host(ronk_ctx* ctx, int op, uint64_t p, const uint64_t* a, uint64_t* out, size_t n) {
+  if (!ctx || (n && (!a || !out))) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (n == 0) return RONK_OK;
+  u64 *da, *db, *dout;
+  RONK_TRY(host_stage(ctx, n, &da, &db, &dout));
+  RONK_CUDA(ctx, cudaMemcpyAsync(da, a, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = (op == 0)   ? ronk_field_neg_u64(ctx, p, da, dout, n)
+           : (op == 1) ? ronk_field_inv_u64(ctx, p, da, dout, n)
+                       : set_err(ctx, RONK_EINVAL, "unknown op");
+  if (rc != RONK_OK) return rc;
+  RONK_CUDA(ctx, cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RONK_OK;
+}
+
+int ronk_field_pow_u64_host(ronk_ctx* ctx, uint64_t p, const uint64_t* a, uint64_t e, uint64_t* out, size_t n) {
+  if (!ctx || (n && (!a || !out))) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (n == 0) return RONK_OK;
+  u64 *da, *db, *dout;
+  RONK_TRY(host_stage(ctx, n, &da, &db, &dout));
+  RONK_CUDA(ctx, cudaMemcpyAsync(da, a, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  RONK_TRY(ronk_field_pow_u64(ctx, p, da, e, dout, n));
+  RONK_CUDA(ctx, cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RONK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+// msm.cu — GF(101²) / AffinePoint<PlutoExtendedCurve> arithmetic and kzg::commit as a Pippenger
+// bucket MSM.  Mirrors src/algebra/field/extension/gf_101_2.rs (inverse :35-47, Mul :86-100),
+// src/curve/mod.rs (Add :178-213, Neg :225-235, Mul<ScalarField> :157-172, is_on_curve :130-139),
+// src/curve/pluto_curve.rs:40-51 (y² = x³ + 3) and src/kzg/setup.rs:48-60 (commit).
+//
+// Points travel as one packed 32-bit word x0 | x1<<8 | y0<<16 | y1<<24 (x = x0 + x1·t);
+// 0xFFFFFFFF is Infinity.  Scalars are F17 residues, one byte each, so a single 5-bit Pippenger
+// window with 16 non-trivial buckets covers the whole scalar.
+//
+//   msm_bucket_kernel   every thread streams its share of (point, scalar) pairs into 16 private
+//                       buckets held in shared memory ([bucket][thread], conflict-free), then the
+//                       CTA tree-reduces each bucket across its threads → partial[cta][17].
+//   msm_finish_kernel   one CTA: per-bucket tree over the partials, then the running-sum
+//                       Σ s·B_s = Σ_{s=16..1} (B_16 + … + B_s), one affine point out.
+// The field is so small that an affine add costs one F101 inversion = x^99 (9 multiplies), cheaper
+// than projective formulas, and it keeps the reference's exceptional-case structure verbatim.
+#include "ronk_internal.h"
+
+namespace ronk {
+
+constexpr u32 Q101 = 101;
+constexpr u32 PT_INF = 0xFFFFFFFFu;
+
+struct Gf { u32 c0, c1; };
+struct Pt { Gf x, y; bool inf; };
+
+RONK_DEV u32 fq_mul(u32 a, u32 b) { return (a * b) % Q101; }
+RONK_DEV u32 fq_add(u32 a, u32 b) { u32 s = a + b; return s >= Q101 ? s - Q101 : s; }
+RONK_DEV u32 fq_sub(u32 a, u32 b) { return a >= b ? a - b : a + Q101 - b; }
+RONK_DEV u32 fq_neg(u32 a) { return a ? Q101 - a : 0; }
+// a^99 = a^-1 (Fermat; prime/mod.rs:62-72).  99 = 0b1100011.
+RONK_DEV u32 fq_inv(u32 a) {
+  const u32 a2 = fq_mul(a, a), a3 = fq_mul(a2, a);
+  const u32 a6 = fq_mul(a3, a3), a12 = fq_mul(a6, a6), a24 = fq_mul(a12, a12);
+  const u32 a48 = fq_mul(a24, a24), a96 = fq_mul(a48, a48);
+  return fq_mul(a96, a3);
+}
+
+RONK_DEV Gf gf_add(Gf a, Gf b) { return {fq_add(a.c0, b.c0), fq_add(a.c1, b.c1)}; }
+RONK_DEV Gf gf_sub(Gf a, Gf b) { return {fq_sub(a.c0, b.c0), fq_sub(a.c1, b.c1)}; }
+RONK_DEV Gf gf_neg(Gf a) { return {fq_neg(a.c0), fq_neg(a.c1)}; }
+RONK_DEV bool gf_eq(Gf a, Gf b) { return a.c0 == b.c0 && a.c1 == b.c1; }
+// (a0 + a1 t)(b0 + b1 t) mod (t² + 2) = (a0b0 - 2a1b1) + (a0b1 + a1b0) t
+RONK_DEV Gf gf_mul(Gf a, Gf b) {
+  return {(a.c0 * b.c0 + 99u * (a.c1 * b.c1 % Q101)) % Q101, (a.c0 * b.c1 + a.c1 * b.c0) % Q101};
+}
+// conj / norm, norm = a0² + 2a1²  (gf_101_2.rs:35-47); caller guarantees a != 0
+RONK_DEV Gf gf_inv(Gf a) {
+  const u32 s = fq_inv((a.c0 * a.c0 + 2u * a.c1 * a.c1) % Q101);
+  return {fq_mul(a.c0, s), fq_mul(fq_neg(a.c1), s)};
+}
+
+RONK_DEV Pt pt_unpack(u32 w) {
+  Pt p;
+  p.inf = (w == PT_INF);
+  p.x = {w & 0xFF, (w >> 8) & 0xFF};
+  p.y = {(w >> 16) & 0xFF, w >> 24};
+  return p;
+}
+RONK_DEV u32 pt_pack(const Pt& p) {
+  return p.inf ? PT_INF : (p.x.c0 | (p.x.c1 << 8) | (p.y.c0 << 16) | (p.y.c1 << 24));
+}
+// Well-formed (canonical coordinates) and on y² = x³ + 3  (curve/mod.rs:130-139).
+RONK_DEV bool pt_valid(u32 w) {
+  if (w == PT_INF) return true;
+  const Pt p = pt_unpack(w);
+  if (p.x.c0 >= Q101 || p.x.c1 >= Q101 || p.y.c0 >= Q101 || p.y.c1 >= Q101) return false;
+  const Gf lhs = gf_mul(p.y, p.y);
+  const Gf rhs = gf_add(gf_mul(gf_mul(p.x, p.x), p.x), Gf{3, 0});
+  return gf_eq(lhs, rhs);
+}
+// AffinePoint + AffinePoint  (curve/mod.rs:178-213), same case order as the reference.
+RONK_DEV Pt pt_add(const Pt& a, const Pt& b) {
+  if (a.inf) return b;
+  if (b.inf) return a;
+  const bool same_x = gf_eq(a.x, b.x);
+  if (same_x && gf_eq(a.y, gf_neg(b.y))) { Pt r; r.inf = true; r.x = {0, 0}; r.y = {0, 0}; return r; }
+  Gf num, den;
+  if (same_x && gf_eq(a.y, b.y)) {  // tangent: 3x² / 2y   (a = 0)
+    num = gf_mul(Gf{3, 0}, gf_mul(a.x, a.x));
+    den = gf_add(a.y, a.y);
+  } else {                          // chord: (y2 - y1) / (x2 - x1)
+    num = gf_sub(b.y, a.y);
+    den = gf_sub(b.x, a.x);
+  }
+  const Gf lam = gf_mul(num, gf_inv(den));
+  Pt r;
+  r.inf = false;
+  r.x = gf_sub(gf_sub(gf_mul(lam, lam), a.x), b.x);
+  r.y = gf_sub(gf_mul(lam, gf_sub(a.x, r.x)), a.y);
+  return r;
+}
+RONK_DEV u32 pt_add_w(u32 a, u32 b) { return pt_pack(pt_add(pt_unpack(a), pt_unpack(b))); }
+
+constexpr int MSM_THREADS = 128;
+
+__global__ void __launch_bounds__(MSM_THREADS) msm_bucket_kernel(const u32* __restrict__ points,
+                                                                 const uint8_t* __restrict__ scalars, size_t n,
+                                                                 u32* __restrict__ partial, int* flag) {
+  __shared__ u32 bucket[17][MSM_THREADS];
+  const u32 t = threadIdx.x;
+#pragma unroll
+  for (int s = 0; s < 17; s++) bucket[s][t] = PT_INF;
+  const size_t stride = (size_t)gridDim.x * MSM_THREADS;
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * MSM_THREADS + t; i < n; i += stride) {
+    const u32 w = points[i];
+    const u32 s = scalars[i];
+    if (s >= 17 || !pt_valid(w)) { bad = true; continue; }
+    if (s == 0 || w == PT_INF) continue;  // g1 * 0 = Infinity (curve/mod.rs:163-165)
+    bucket[s][t] = pt_add_w(bucket[s][t], w);
+  }
+  if (bad) atomicExch(flag, 1);
+  __syncthreads();
+  for (u32 half = MSM_THREADS / 2; half > 0; half >>= 1) {
+    if (t < half) {
+#pragma unroll 1
+      for (int s = 1; s < 17; s++) bucket[s][t] = pt_add_w(bucket[s][t], bucket[s][t + half]);
+    }
+    __syncthreads();
+  }
+  if (t < 17) partial[(size_t)blockIdx.x * 17 + t] = bucket[t][0];
+}
+
+// partial[sets][17] → buckets_out[17], result.  blockDim = 17 warps.
+__global__ void __launch_bounds__(17 * 32) msm_finish_kernel(const u32* __restrict__ partial, u32 sets,
+                                                             u32* __restrict__ buckets_out, u32* __restrict__ result) {
+  __shared__ u32 B[17];
+  const u32 s = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  u32 acc = PT_INF;
+  for (u32 g = lane; g < sets; g += 32) acc = pt_add_w(acc, partial[(size_t)g * 17 + s]);
+  for (int off = 16; off > 0; off >>= 1) {
+    const u32 other = __shfl_down_sync(0xFFFFFFFFu, acc, off);
+    acc = pt_add_w(acc, other);
+  }
+  if (lane == 0) { B[s] = (s == 0) ? PT_INF : acc; buckets_out[s] = B[s]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 run = PT_INF, tot = PT_INF;
+    for (int k = 16; k >= 1; k--) {
+      run = pt_add_w(run, B[k]);
+      tot = pt_add_w(tot, run);
+    }
+    result[0] = tot;
+  }
+}
+
+// element-wise curve ops (host API support). op: 0 add, 1 neg, 2 scalar-mul by repeated addition
+__global__ void point_op_kernel(int op, const u32* a, const u32* b, const uint8_t* sc, u32* out, size_t n, int* flag) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u32 wa = a[i];
+    if (!pt_valid(wa)) { atomicExch(flag, 1); out[i] = PT_INF; continue; }
+    if (op == 0) {
+      const u32 wb = b[i];
+      if (!pt_valid(wb)) { atomicExch(flag, 1); out[i] = PT_INF; continue; }
+      out[i] = pt_add_w(wa, wb);
+    } else if (op == 1) {
+      Pt p = pt_unpack(wa);
+      if (!p.inf) p.y = gf_neg(p.y);  // curve/mod.rs:228-231
+      out[i] = pt_pack(p);
+    } else {
+      const u32 s = sc[i];
+      if (s >= 17) { atomicExch(flag, 1); out[i] = PT_INF; continue; }
+      u32 val = PT_INF;              // rhs == 0 → Infinity
+      if (s) {
+        val = wa;
+        for (u32 k = 1; k < s; k++) val = pt_add_w(val, wa);  // (s-1) repeated `+=`
+      }
+      out[i] = val;
+    }
+  }
+}
+
+static int msm_grid(ronk_ctx* ctx, size_t n) {
+  size_t ctas = (n + (size_t)MSM_THREADS * 32 - 1) / ((size_t)MSM_THREADS * 32);
+  const size_t cap = (size_t)ctx->sm_count * 4;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  return (int)ctas;
+}
+
+// device buckets[17] + result[1] for the first n_scalars terms
+static int msm_device(ronk_ctx* ctx, const uint8_t* points, size_t n_points, const uint8_t* scalars, size_t n_scalars,
+                      u32* h_buckets /*17 or null*/, u32* h_result) {
+  if (!ctx || (n_scalars && (!points || !scalars))) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (n_points < n_scalars) return set_err(ctx, RONK_EINVAL, "srs shorter than coefficients (kzg/setup.rs:53)");
+  if (((uintptr_t)points & 3) != 0) return set_err(ctx, RONK_EINVAL, "points must be 4-byte aligned");
+  const int ctas = msm_grid(ctx, n_scalars);
+  const size_t need = ((size_t)ctas * 17 + 17 + 1) * sizeof(u32);
+  RONK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, need));
+  u32* partial = (u32*)ctx->ws;
+  u32* d_buckets = partial + (size_t)ctas * 17;
+  u32* d_result = d_buckets + 17;
+  RONK_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+  {
+    LaunchScope ls(ctx, "msm_bucket");
+    msm_bucket_kernel<<<ctas, MSM_THREADS, 0, ctx->stream>>>((const u32*)points, scalars, n_scalars, partial,
+                                                            ctx->d_flag);
+  }
+  RONK_TRY(check_launch(ctx, "msm_bucket_kernel"));
+  {
+    LaunchScope ls(ctx, "msm_finish");
+    msm_finish_kernel<<<1, 17 * 32, 0, ctx->stream>>>(partial, (u32)ctas, d_buckets, d_result);
+  }
+  RONK_TRY(check_launch(ctx, "msm_finish_kernel"));
+  u32 host[18];
+  RONK_CUDA(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_CUDA(ctx, cudaMemcpyAsync(host, d_buckets, 18 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (*ctx->h_flag) return set_err(ctx, RONK_EINVAL, "off-curve point, non-canonical coordinate or scalar >= 17");
+  if (h_buckets) std::memcpy(h_buckets, host, 17 * sizeof(u32));
+  if (h_result) *h_result = host[17];
+  return RONK_OK;
+}
+
+static void unpack_to_bytes(u32 w, uint8_t out[4]) {
+  out[0] = (uint8_t)(w & 0xFF);
+  out[1] = (uint8_t)((w >> 8) & 0xFF);
+  out[2] = (uint8_t)((w >> 16) & 0xFF);
+  out[3] = (uint8_t)(w >> 24);
+}
+
+struct DevBytes {
+  void* p = nullptr;
+  ~DevBytes() { if (p) cudaFree(p); }
+};
+
+}  // namespace ronk
+
+using namespace ronk;
+
+extern "C" {
+
+int ronk_msm_pluto_ext(ronk_ctx* ctx, const uint8_t* points, size_t n_points, const uint8_t* scalars, size_t n_scalars,
+                       uint8_t out[4]) {
+  if (!out) return set_err(ctx, RONK_EINVAL, "null argument");
+  u32 res = PT_INF;
+  RONK_TRY(msm_device(ctx, points, n_points, scalars, n_scalars, nullptr, &res));
+  unpack_to_bytes(res, out);
+  return RONK_OK;
+}
+
+int ronk_msm_pluto_ext_buckets(ronk_ctx* ctx, const uint8_t* points, size_t n_points, const uint8_t* scalars,
+                               size_t n_scalars, uint8_t buckets[68]) {
+  if (!buckets) return set_err(ctx, RONK_EINVAL, "null argument");
+  u32 b[17];
+  RONK_TRY(msm_device(ctx, points, n_points, scalars, n_scalars, b, nullptr));
+  for (int s = 0; s < 17; s++) unpack_to_bytes(b[s], buckets + 4 * s);
+  return RONK_OK;
+}
+
+int ronk_msm_pluto_ext_host(ronk_ctx* ctx, const uint8_t* points, size_t n_points, const uint8_t* scalars,
+                            size_t n_scalars, uint8_t out[4]) {
+  if (!ctx || !out || (n_scalars && (!points || !scalars))) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (n_points < n_scalars) return set_err(ctx, RONK_EINVAL, "srs shorter than coefficients (kzg/setup.rs:53)");
+  DevBytes P, S;
+  RONK_CUDA(ctx, cudaMalloc(&P.p, n_scalars * 4 + 4));
+  RONK_CUDA(ctx, cudaMalloc(&S.p, n_scalars + 4));
+  RONK_CUDA(ctx, cudaMemcpyAsync(P.p, points, n_scalars * 4, cudaMemcpyHostToDevice, ctx->stream));
+  RONK_CUDA(ctx, cudaMemcpyAsync(S.p, scalars, n_scalars, cudaMemcpyHostToDevice, ctx->stream));
+  return ronk_msm_pluto_ext(ctx, (const uint8_t*)P.p, n_scalars, (const uint8_t*)S.p, n_scalars, out);
+}
+
+int ronk_msm_combine_buckets_host(ronk_ctx* ctx, const uint8_t* buckets, size_t n_sets, uint8_t out[4]) {
+  if (!ctx || !out || (n_sets && !buckets)) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (n_sets > (1u << 20)) return set_err(ctx, RONK_EUNSUPPORTED, "too many bucket sets");
+  const size_t words = n_sets * 17;
+  RONK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, (words + 18) * sizeof(u32)));
+  u32* partial = (u32*)ctx->ws;
+  u32* d_buckets = partial + words;
+  u32* d_result = d_buckets + 17;
+  if (words) RONK_CUDA(ctx, cudaMemcpyAsync(partial, buckets, words * 4, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    LaunchScope ls(ctx, "msm_finish");
+    msm_finish_kernel<<<1, 17 * 32, 0, ctx->stream>>>(partial, (u32)n_sets, d_buckets, d_result);
+  }
+  RONK_TRY(check_launch(ctx, "msm_finish_kernel"));
+  u32 res;
+  RONK_CUDA(ctx, cudaMemcpyAsync(&res, d_result, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  unpack_to_bytes(res, out);
+  return RONK_OK;
+}
+
+static int point_op_host(ronk_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, const uint8_t* sc, uint8_t* out,
+                         size_t n) {
+  if (!ctx || (n && (!a || !out)) || (n && op == 0 && !b) || (n && op == 2 && !sc))
+    return set_err(ctx, RONK_EINVAL, "null argument");
+  if (n == 0) return RONK_OK;
+  DevBytes A, B, S, O;
+  RONK_CUDA(ctx, cudaMalloc(&A.p, n * 4));
+  RONK_CUDA(ctx, cudaMalloc(&O.p, n * 4));
+  RONK_CUDA(ctx, cudaMemcpyAsync(A.p, a, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (op == 0) {
+    RONK_CUDA(ctx, cudaMalloc(&B.p, n * 4));
+    RONK_CUDA(ctx, cudaMemcpyAsync(B.p, b, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (op == 2) {
+    RONK_CUDA(ctx, cudaMalloc(&S.p, n));
+    RONK_CUDA(ctx, cudaMemcpyAsync(S.p, sc, n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  RONK_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+  size_t blocks = (n + 127) / 128;
+  if (blocks > (size_t)ctx->sm_count * 8) blocks = (size_t)ctx->sm_count * 8;
+  {
+    LaunchScope ls(ctx, "point_op");
+    point_op_kernel<<<(int)blocks, 128, 0, ctx->stream>>>(op, (const u32*)A.p, (const u32*)B.p, (const uint8_t*)S.p,
+                                                         (u32*)O.p, n, ctx->d_flag);
+  }
+  RONK_TRY(check_launch(ctx, "point_op_kernel"));
+  RONK_CUDA(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_CUDA(ctx, cudaMemcpyAsync(out, O.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (*ctx->h_flag) return set_err(ctx, RONK_EINVAL, "Point is not on curve / scalar out of range");
+  return RONK_OK;
+}
+
+int ronk_point_add_pluto_ext_host(ronk_ctx* ctx, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  return point_op_host(ctx, 0, a, b, nullptr, out, n);
+}
+int ronk_point_neg_pluto_ext_host(ronk_ctx* ctx, const uint8_t* a, uint8_t* out, size_t n) {
+  return point_op_host(ctx, 1, a, nullptr, nullptr, out, n);
+}
+int ronk_point_smul_pluto_ext_host(ronk_ctx* ctx, const uint8_t* a, const uint8_t* scalars, uint8_t* out, size_t n) {
+  return point_op_host(ctx, 2, a, nullptr, scalars, out, n);
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// ntt.cu — plans (twiddle tables) and launches for the tiled NTT kernel.
+// Public entry points: ronk_ntt_u64, ronk_ntt_mul_u64, ronk_ntt_u64_host (include/ronk_b200.h),
+// replacing Polynomial::fft / ifft (src/polynomial/mod.rs:273-323, :430-484).
+#include <cstdlib>
+
+#include "ntt_kernel.cuh"
+#include "ronk_internal.h"
+
+namespace ronk {
+
+int make_mont_field(ronk_ctx* ctx, u64 p, u64 g, bool inverse, MontField* out) {
+  if (!(p & 1) || p < 3) return set_err(ctx, RONK_EUNSUPPORTED, "modulus must be an odd prime");
+  MontField f;
+  f.p = p;
+  f.pinv = h_inv64(p);
+  const u64 r1 = (u64)((((unsigned __int128)1) << 64) % p);
+  f.r2 = h_mulmod(r1, r1, p);
+  for (int e = 0; e < 8; e++) f.w16t[e] = r1;
+  if (g) {
+    u32 k = 0;
+    while (k < 4 && ((p - 1) >> k) % 2 == 0) k++;
+    if (k) {
+      u64 w = h_powmod(g, (p - 1) >> k, p);                  // primitive 2^k-th root
+      if (inverse) w = h_powmod(w, ((u64)1 << k) - 1, p);    // its inverse
+      const int stride = 16 >> k;
+      for (int e = 0; e < 8; e++)
+        if (e % stride == 0) f.w16t[e] = h_mulmod(h_powmod(w, e / stride, p), r1, p);
+    }
+  }
+  *out = f;
+  return RONK_OK;
+}
+
+template <class F>
+static int build_table(ronk_ctx* ctx, const F& f, u64 w, u64 s, u64** tab, u32 count) {
+  RONK_CUDA(ctx, cudaMalloc((void**)tab, (size_t)count * sizeof(u64)));
+  {
+    LaunchScope ls(ctx, "pow_table");
+    pow_table_kernel<F><<<(count + 255) / 256, 256, 0, ctx->stream>>>(f, w, s, *tab, count);
+  }
+  return check_launch(ctx, "pow_table_kernel");
+}
+
+template <class F>
+static int build_plan(ronk_ctx* ctx, const F& f, u64 p, u64 g, u32 log_n, NttPlan* plan) {
+  const u64 n = (u64)1 << log_n;
+  const u64 w = h_powmod(g, (p - 1) / n, p);
+  const u64 ninv = h_powmod(n % p, p - 2, p);
+  plan->p = p;
+  plan->g = g;
+  plan->log_n = log_n;
+  const NttShape sh = ntt_shape(log_n);
+  if (!sh.two_pass) {
+    plan->two_pass = false;
+    RONK_TRY(build_table(ctx, f, w, 1, &plan->tw1, (u32)n));
+  } else {
+    plan->two_pass = true;
+    plan->log_n1 = sh.log_n1;
+    plan->log_n2 = sh.log_n2;
+    const u64 n1 = (u64)1 << plan->log_n1, n2 = (u64)1 << plan->log_n2;
+    RONK_TRY(build_table(ctx, f, h_powmod(w, n2, p), 1, &plan->tw1, (u32)n1));
+    RONK_TRY(build_table(ctx, f, h_powmod(w, n1, p), 1, &plan->tw2, (u32)n2));
+    RONK_TRY(build_table(ctx, f, w, 1, &plan->tw_lo, (u32)n1));
+    RONK_TRY(build_table(ctx, f, h_powmod(w, n1, p), ninv, &plan->tw_hi_inv, (u32)n2));
+  }
+  // n^-1 in twiddle form: Goldilocks → plain; Montgomery → ninv·R mod p
+  if (p == GL_P && g == 7) plan->scale_inv = ninv;
+  else plan->scale_inv = h_mulmod(ninv, (u64)((((unsigned __int128)1) << 64) % p), p);
+  return RONK_OK;
+}
+
+template <class F, int MODE, bool INV>
+static int launch_tile(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
+  const u32 T = 1u << A.tile_log;
+  const size_t smem = (size_t)T * sizeof(u64);
+  static bool attr_done = false;  // one device per process in practice; re-set is harmless
+  if (!attr_done || smem > 48 * 1024) {
+    RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_tile_kernel<F, MODE, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        128 * 1024));
+    attr_done = true;
+  }
+  {
+    LaunchScope ls(ctx, name);
+    ntt_tile_kernel<F, MODE, INV><<<tiles, T / 16, smem, ctx->stream>>>(f, A);
+  }
+  return check_launch(ctx, name);
+}
+
+template <class F, bool INV>
+static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, const u64* mul, u32 batch) {
+  const u32 log_n = pl.log_n;
+  u64 tiles = 0;
+  if (!pl.two_pass) {
+    u32 cap = 12;
+    if (const char* s = getenv("RONK_SINGLE_TILE_LOG")) cap = (u32)atoi(s);
+    const NttTileArgs A =
+        ntt_args_single(data, mul, pl.tw1, pl.scale_inv, log_n, (u64)batch << log_n, INV, cap, &tiles);
+    if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
+    return launch_tile<F, MODE_SINGLE, INV>(ctx, f, A, (u32)tiles, INV ? "intt_single" : "ntt_single");
+  }
+  const size_t bytes = ((size_t)batch << log_n) * sizeof(u64);
+  RONK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, bytes));
+  // pass 1: N1-point transforms down the columns, inter-pass twiddle, blocked write to the workspace
+  const NttTileArgs A1 =
+      ntt_args_pass1(data, (u64*)ctx->ws, pl.tw1, pl.tw_lo, INV ? pl.tw_hi_inv : pl.tw2, log_n, batch, &tiles);
+  if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
+  RONK_TRY((launch_tile<F, MODE_PASS1, INV>(ctx, f, A1, (u32)tiles, INV ? "intt_pass1" : "ntt_pass1")));
+  // pass 2: N2-point transforms along the contiguous workspace tiles, natural-order output
+  const NttTileArgs A2 = ntt_args_pass2((const u64*)ctx->ws, data, mul, pl.tw2, log_n, batch, &tiles);
+  if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
+  return launch_tile<F, MODE_PASS2, INV>(ctx, f, A2, (u32)tiles, INV ? "intt_pass2" : "ntt_pass2");
+}
+
+template <class F>
+static int ntt_with_field(ronk_ctx* ctx, const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 log_n, u32 batch,
+                          int inverse) {
+  auto key = std::make_tuple((uint64_t)p, (uint64_t)g, (uint32_t)log_n);
+  auto it = ctx->plans.find(key);
+  if (it == ctx->plans.end()) {
+    NttPlan pl;
+    RONK_TRY(build_plan(ctx, f, p, g, log_n, &pl));
+    it = ctx->plans.emplace(key, pl).first;
+  }
+  return inverse ? run_ntt<F, true>(ctx, f, it->second, data, mul, batch)
+                 : run_ntt<F, false>(ctx, f, it->second, data, mul, batch);
+}
+
+int ntt_device(ronk_ctx* ctx, u64 p, u64 g, u64* data, const u64* mul, u32 log_n, u32 batch, int inverse) {
+  if (!ctx || !data) return set_err(ctx, RONK_EINVAL, "null argument");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (g == 0 || g >= p) return set_err(ctx, RONK_EINVAL, "generator out of range");
+  if (log_n > 28) return set_err(ctx, RONK_EUNSUPPORTED, "log_n > 28 not supported");
+  if (log_n >= 64 || (p - 1) % ((u64)1 << log_n) != 0)
+    return set_err(ctx, RONK_EINVAL, "n must divide p - 1 (no primitive n-th root of unity)");
+  if (batch == 0) return RONK_OK;
+  if (log_n == 0) {
+    if (mul) return ronk_field_mul_u64(ctx, p, (const uint64_t*)data, (const uint64_t*)mul, (uint64_t*)data, batch);
+    return RONK_OK;
+  }
+  if (is_goldilocks_fast(p, g)) {
+    GoldilocksField f;
+    return ntt_with_field(ctx, f, p, g, data, mul, log_n, batch, inverse);
+  }
+  MontField f;
+  RONK_TRY(make_mont_field(ctx, p, g, inverse != 0, &f));
+  return ntt_with_field(ctx, f, p, g, data, mul, log_n, batch, inverse);
+}
+
+}  // namespace ronk
+
+using namespace ronk;
+
+extern "C" int ronk_ntt_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* data, uint32_t log_n, uint32_t batch,
+                            int inverse) {
+  return ntt_device(ctx, p, g, (u64*)data, nullptr, log_n, batch, inverse);
+}
+
+extern "C" int ronk_ntt_mul_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* data, const uint64_t* mul,
+                                uint32_t log_n, uint32_t batch) {
+  if (!mul) return set_err(ctx, RONK_EINVAL, "null multiplier");
+  return ntt_device(ctx, p, g, (u64*)data, (const u64*)mul, log_n, batch, 0);
+}
+
+extern "C" int ronk_ntt_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* host_data, uint32_t log_n,
+                                 uint32_t batch, int inverse) {
+  if (!ctx || !host_data) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (log_n > 28) return set_err(ctx, RONK_EUNSUPPORTED, "log_n > 28 not supported");
+  const size_t bytes = ((size_t)batch << log_n) * sizeof(u64);
+  if (bytes == 0) return RONK_OK;
+  RONK_TRY(ensure_ws(ctx, &ctx->ws2, &ctx->ws2_bytes, bytes));
+  RONK_CUDA(ctx, cudaMemcpyAsync(ctx->ws2, host_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  RONK_TRY(ntt_device(ctx, p, g, (u64*)ctx->ws2, nullptr, log_n, batch, inverse));
+  RONK_CUDA(ctx, cudaMemcpyAsync(host_data, ctx->ws2, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RONK_OK;
+}

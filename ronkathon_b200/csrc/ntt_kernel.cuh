@@ -1,0 +1,339 @@
+// ntt_kernel.cuh — the tiled number-theoretic transform kernel (sm_100a).
+//
+// Replaces Polynomial::fft / ifft (src/polynomial/mod.rs:273-323, :430-484): same map
+// X[k] = Σ_j a_j ω^(jk), natural order in and out, canonical residues — computed as a
+// decimation-in-frequency transform on a shared-memory tile instead of the reference's recursion.
+//
+// One CTA owns a tile of T = 2^tile_log field elements (≤ 2^14 = 128 KiB of shared memory) and
+// T/16 threads.  Tile index e = [batch-in-tile | NTT index i (log_m bits) | column c (log_c bits)].
+// The transform runs over the i bits in "rounds": every thread pulls 16 elements that differ in a
+// 4-bit window of i into registers, does a radix-16 DIF butterfly network there (inner twiddles are
+// 16th roots of unity — shifts for Goldilocks), multiplies by one general twiddle ω_L^(i2·k1) from a
+// table, and writes back in place.  After the last round position i holds X[bitrev(i)]; the store
+// phase undoes that permutation for free while it streams the tile out.
+//
+// Three modes share the code:
+//   MODE_SINGLE  n ≤ T: whole transforms inside one tile (several per tile when n < T).
+//   MODE_PASS1   n = N1·N2 > T, first pass: tile = all N1 rows × C adjacent columns of the N1×N2
+//                matrix view (x[j1·N2 + j2]); N1-point transforms down the columns, then the
+//                inter-pass twiddle ω_n^(j2·k1), written to the workspace in the blocked layout
+//                W[k1 / C2][j2][k1 % C2] so that pass 2 reads whole contiguous tiles.
+//   MODE_PASS2   tile = C2 adjacent k1 × all N2 values of j2 (contiguous in W); N2-point
+//                transforms, results to X[k1 + N1·k2] (natural order), optional fused point-wise
+//                multiply.
+// Only the compulsory input read (pass 1) and output write (pass 2) touch HBM in C·8-byte
+// segments; both workspace transfers are fully contiguous.
+#pragma once
+#include <utility>
+
+#include "field.cuh"
+
+namespace ronk {
+
+enum { MODE_SINGLE = 0, MODE_PASS1 = 1, MODE_PASS2 = 2 };
+enum { NTT_FLAG_SCALE = 1, NTT_FLAG_MUL = 2 };
+
+struct NttTileArgs {
+  const u64* src;
+  u64* dst;
+  const u64* tw_tile;  // ω_M^e, e ∈ [0, M), twiddle form (M = 2^log_m)
+  const u64* tw_lo;    // PASS1: ω_n^x, x ∈ [0, 2^log_lo)
+  const u64* tw_hi;    // PASS1: ω_n^(y·2^log_lo) (· n^-1 for the inverse), y ∈ [0, n >> log_lo)
+  const u64* mul_src;  // optional point-wise multiplier, indexed like dst
+  u64 scale;           // SINGLE + inverse: n^-1 in twiddle form
+  u64 total;           // SINGLE: number of valid elements (batch·n)
+  u32 tile_log, log_m, log_c;
+  u32 log_n, log_n1, log_n2, log_c2, log_lo;
+  u32 tiles_per_batch;
+  u32 flags;
+};
+
+// Shared-memory swizzle: 64-bit accesses are served per half-warp against 16 eight-byte banks
+// (low 4 bits of the element index).  XOR-folding bits [4,8), [8,12) and [12,14) into the bank
+// bits makes every access pattern of this kernel (window at any bit position, digit-reversed
+// store) hit 16 distinct banks per half-warp.
+RONK_DEV u32 swz(u32 e) { return e ^ (((e >> 4) ^ (e >> 8)) & 15u) ^ (((e >> 12) & 3u) << 2); }
+
+RONK_DEV u32 bitrev(u32 v, u32 bits) {
+#if defined(__CUDA_ARCH__)
+  return bits ? (__brev(v) >> (32 - bits)) : 0;
+#else
+  u32 r = 0;
+  for (u32 i = 0; i < bits; i++) r |= ((v >> i) & 1u) << (bits - 1 - i);
+  return r;
+#endif
+}
+RONK_DEV u64 ld_tw(const u64* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+// One radix-2 DIF butterfly level on register bit BETA of a 16-element register tile.
+template <int BETA, int Q, bool INV, class F>
+RONK_DEV void bf_one(const F& f, u64 (&x)[16]) {
+  constexpr int h = 1 << BETA;
+  if constexpr ((Q & h) == 0) {
+    u64 a = x[Q], b = x[Q + h];
+    x[Q] = f.add(a, b);
+    x[Q + h] = f.template w16<(Q & (h - 1)) * (8 / h), INV>(f.sub(a, b));
+  }
+}
+template <int BETA, bool INV, class F, int... Q>
+RONK_DEV void bf_level(const F& f, u64 (&x)[16], std::integer_sequence<int, Q...>) {
+  (bf_one<BETA, Q, INV>(f, x), ...);
+}
+// NST active levels on the low NST bits of the register index (NST = 4: full radix-16).
+template <int NST, bool INV, class F>
+RONK_DEV void radix_network(const F& f, u64 (&x)[16]) {
+  using seq = std::make_integer_sequence<int, 16>;
+  if constexpr (NST >= 4) bf_level<3, INV>(f, x, seq{});
+  if constexpr (NST >= 3) bf_level<2, INV>(f, x, seq{});
+  if constexpr (NST >= 2) bf_level<1, INV>(f, x, seq{});
+  if constexpr (NST >= 1) bf_level<0, INV>(f, x, seq{});
+}
+
+// One round: gather the window [wb, wb+4) of the tile index into registers, butterfly, twiddle,
+// scatter back in place.  `lcur` = log2 of the current sub-transform length (only used when NST==4).
+template <int NST, bool INV, class F>
+RONK_DEV void ntt_round(const F& f, u64* smem, const NttTileArgs& A, u32 wb, u32 lcur, u32 t) {
+  const u32 lowmask = (1u << wb) - 1u;
+  const u32 e0 = ((t >> wb) << (wb + 4)) | (t & lowmask);
+  u64 x[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) x[q] = smem[swz(e0 | ((u32)q << wb))];
+  radix_network<NST, INV>(f, x);
+  if (NST == 4 && lcur > 4) {
+    const u32 M1 = (1u << A.log_m) - 1u;
+    const u32 i2 = (e0 >> A.log_c) & ((1u << (lcur - 4)) - 1u);
+    const u32 step = i2 << (A.log_m - lcur);
+#pragma unroll
+    for (int j = 1; j < 16; j++) {
+      const u32 k1 = ((j & 1) << 3) | ((j & 2) << 1) | ((j & 4) >> 1) | ((j & 8) >> 3);
+      u32 idx = (step * k1) & M1;
+      if (INV) idx = (0u - idx) & M1;
+      x[j] = f.mul_tw(x[j], ld_tw(A.tw_tile + idx));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 16; q++) smem[swz(e0 | ((u32)q << wb))] = x[q];
+}
+
+// ---------------- load phase: HBM → shared ----------------
+template <class F, int MODE>
+RONK_DEV void ntt_load_phase(u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
+  const u32 T = 1u << A.tile_log;
+  u32 b = 0, sub = tile;
+  if (MODE != MODE_SINGLE) {
+    b = tile / A.tiles_per_batch;
+    sub = tile - b * A.tiles_per_batch;
+  }
+  if (MODE == MODE_SINGLE) {
+    const u64 base = (u64)tile << A.tile_log;
+    for (u32 e = tid; e < T; e += nthr) {
+      const u64 g = base + e;
+      smem[swz(e)] = (g < A.total) ? A.src[g] : 0ULL;
+    }
+  } else if (MODE == MODE_PASS1) {
+    const u64 base = ((u64)b << A.log_n) + ((u64)sub << A.log_c);
+    const u32 cmask = (1u << A.log_c) - 1u;
+    for (u32 e = tid; e < T; e += nthr) {
+      const u32 j1 = e >> A.log_c, c = e & cmask;
+      smem[swz(e)] = A.src[base + ((u64)j1 << A.log_n2) + c];
+    }
+  } else {
+    const u64 base = ((u64)b << A.log_n) + ((u64)sub << A.tile_log);
+    for (u32 e = tid; e < T; e += nthr) smem[swz(e)] = A.src[base + e];
+  }
+}
+
+// Round schedule: full radix-16 rounds from the top of the NTT index down, then one partial
+// round for the remaining 1–3 bits.  Returns false when there is no round `r`.
+RONK_DEV bool ntt_round_plan(const NttTileArgs& A, u32 r, u32* nst, u32* wb, u32* lcur) {
+  const u32 full = A.log_m / 4, rem = A.log_m % 4;
+  if (r < full) {
+    *nst = 4;
+    *lcur = A.log_m - 4 * r;
+    *wb = A.log_c + *lcur - 4;
+    return true;
+  }
+  if (r == full && rem) {
+    *nst = rem;
+    *lcur = rem;
+    *wb = A.log_c;
+    return true;
+  }
+  return false;
+}
+
+template <class F, bool INV>
+RONK_DEV void ntt_round_dispatch(const F& f, u64* smem, const NttTileArgs& A, u32 nst, u32 wb, u32 lcur, u32 tid) {
+  if (nst == 4) ntt_round<4, INV>(f, smem, A, wb, lcur, tid);
+  else if (nst == 3) ntt_round<3, INV>(f, smem, A, wb, 0, tid);
+  else if (nst == 2) ntt_round<2, INV>(f, smem, A, wb, 0, tid);
+  else ntt_round<1, INV>(f, smem, A, wb, 0, tid);
+}
+
+// ---------------- store phase: shared → HBM (un-bit-reverse on the fly) ----------------
+template <class F, int MODE, bool INV>
+RONK_DEV void ntt_store_phase(const F& f, const u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
+  const u32 T = 1u << A.tile_log;
+  const u32 M = 1u << A.log_m;
+  u32 b = 0, sub = tile;
+  if (MODE != MODE_SINGLE) {
+    b = tile / A.tiles_per_batch;
+    sub = tile - b * A.tiles_per_batch;
+  }
+  if (MODE == MODE_SINGLE) {
+    const u64 base = (u64)tile << A.tile_log;
+    for (u32 g = tid; g < T; g += nthr) {
+      if (base + g >= A.total) continue;
+      const u32 bt = g >> A.log_m, k = g & (M - 1u);
+      const u32 e = (bt << A.log_m) | bitrev(k, A.log_m);
+      u64 v = smem[swz(e)];
+      if (A.flags & NTT_FLAG_SCALE) v = f.mul_tw(v, A.scale);
+      if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[base + g]);
+      A.dst[base + g] = v;
+    }
+  } else if (MODE == MODE_PASS1) {
+    const u32 lc = A.log_c, lc2 = A.log_c2;
+    const u32 chunk_log = lc + lc2;
+    const u32 nmask = (A.log_n >= 32) ? 0xFFFFFFFFu : ((1u << A.log_n) - 1u);
+    const u32 lomask = (1u << A.log_lo) - 1u;
+    const u64 base = (u64)b << A.log_n;
+    for (u32 g = tid; g < T; g += nthr) {
+      const u32 k1_blk = g >> chunk_log;
+      const u32 rem = g & ((1u << chunk_log) - 1u);
+      const u32 c = rem >> lc2, k1_in = rem & ((1u << lc2) - 1u);
+      const u32 k1 = (k1_blk << lc2) | k1_in;
+      const u32 e = (bitrev(k1, A.log_m) << lc) | c;
+      const u32 j2 = (sub << lc) | c;
+      u32 ex = j2 * k1;
+      if (INV) ex = (0u - ex) & nmask;
+      const u64 w = f.mul_tw(ld_tw(A.tw_lo + (ex & lomask)), ld_tw(A.tw_hi + (ex >> A.log_lo)));
+      const u64 v = f.mul_tw(smem[swz(e)], w);
+      A.dst[base + ((u64)k1_blk << (A.log_n2 + lc2)) + ((u64)j2 << lc2) + k1_in] = v;
+    }
+  } else {
+    const u32 lc2 = A.log_c;  // pass-2 tile: columns are the C2 adjacent k1 values
+    const u64 base = ((u64)b << A.log_n) + ((u64)sub << lc2);
+    for (u32 g = tid; g < T; g += nthr) {
+      const u32 k2 = g >> lc2, k1_in = g & ((1u << lc2) - 1u);
+      const u32 e = (bitrev(k2, A.log_m) << lc2) | k1_in;
+      const u64 addr = base + k1_in + ((u64)k2 << A.log_n1);
+      u64 v = smem[swz(e)];
+      if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[addr]);
+      A.dst[addr] = v;
+    }
+  }
+}
+
+// ---------------- launch geometry (host; shared by ntt.cu and the CPU emulator in tests/emu) -------------
+struct NttShape {
+  bool two_pass;
+  u32 log_n1, log_n2;  // n = N1·N2, N1 ≥ N2 (two-pass only)
+};
+inline NttShape ntt_shape(u32 log_n) {
+  NttShape s;
+  s.two_pass = log_n > 14;
+  s.log_n1 = s.two_pass ? (log_n + 1) / 2 : log_n;
+  s.log_n2 = s.two_pass ? log_n / 2 : 0;
+  return s;
+}
+constexpr u32 NTT_TILE_LOG_MAX = 14;
+
+// Whole transforms inside one tile.  tile_cap = preferred tile size (log2) when several small
+// transforms share a tile.
+inline NttTileArgs ntt_args_single(u64* data, const u64* mul, const u64* tw, u64 scale_inv, u32 log_n, u64 total,
+                                   bool inverse, u32 tile_cap, u64* tiles) {
+  NttTileArgs A = {};
+  u32 want = 0;
+  while (((u64)1 << want) < total) want++;
+  if (want > tile_cap) want = tile_cap;
+  u32 tile_log = log_n;
+  if (tile_log < want) tile_log = want;
+  if (tile_log < 9) tile_log = 9;
+  if (tile_log > NTT_TILE_LOG_MAX) tile_log = NTT_TILE_LOG_MAX;
+  A.src = data;
+  A.dst = data;
+  A.tw_tile = tw;
+  A.mul_src = mul;
+  A.scale = scale_inv;
+  A.total = total;
+  A.tile_log = tile_log;
+  A.log_m = log_n;
+  A.log_c = 0;
+  A.log_n = log_n;
+  A.flags = (inverse ? NTT_FLAG_SCALE : 0) | (mul ? NTT_FLAG_MUL : 0);
+  *tiles = (total + ((u64)1 << tile_log) - 1) >> tile_log;
+  return A;
+}
+inline NttTileArgs ntt_args_pass1(const u64* data, u64* ws, const u64* tw1, const u64* tw_lo, const u64* tw_hi,
+                                  u32 log_n, u32 batch, u64* tiles) {
+  const NttShape sh = ntt_shape(log_n);
+  NttTileArgs A = {};
+  A.src = data;
+  A.dst = ws;
+  A.tw_tile = tw1;
+  A.tw_lo = tw_lo;
+  A.tw_hi = tw_hi;
+  A.tile_log = NTT_TILE_LOG_MAX;
+  A.log_m = sh.log_n1;
+  A.log_c = NTT_TILE_LOG_MAX - sh.log_n1;
+  A.log_n = log_n;
+  A.log_n1 = sh.log_n1;
+  A.log_n2 = sh.log_n2;
+  A.log_c2 = NTT_TILE_LOG_MAX - sh.log_n2;
+  A.log_lo = sh.log_n1;
+  A.tiles_per_batch = 1u << (sh.log_n2 - A.log_c);
+  *tiles = (u64)batch * A.tiles_per_batch;
+  return A;
+}
+inline NttTileArgs ntt_args_pass2(const u64* ws, u64* data, const u64* mul, const u64* tw2, u32 log_n, u32 batch,
+                                  u64* tiles) {
+  const NttShape sh = ntt_shape(log_n);
+  NttTileArgs A = {};
+  A.src = ws;
+  A.dst = data;
+  A.tw_tile = tw2;
+  A.mul_src = mul;
+  A.tile_log = NTT_TILE_LOG_MAX;
+  A.log_m = sh.log_n2;
+  A.log_c = NTT_TILE_LOG_MAX - sh.log_n2;
+  A.log_n = log_n;
+  A.log_n1 = sh.log_n1;
+  A.log_n2 = sh.log_n2;
+  A.log_c2 = A.log_c;
+  A.log_lo = sh.log_n1;
+  A.tiles_per_batch = 1u << (sh.log_n1 - A.log_c);
+  A.flags = mul ? NTT_FLAG_MUL : 0;
+  *tiles = (u64)batch * A.tiles_per_batch;
+  return A;
+}
+
+#if defined(__CUDACC__)
+template <class F, int MODE, bool INV>
+__global__ void __launch_bounds__(1024, 1) ntt_tile_kernel(const F f, const NttTileArgs A) {
+  extern __shared__ __align__(16) u64 smem[];
+  const u32 nthr = blockDim.x, tid = threadIdx.x, tile = blockIdx.x;
+  ntt_load_phase<F, MODE>(smem, A, tile, tid, nthr);
+  __syncthreads();
+  u32 nst, wb, lcur;
+  for (u32 r = 0; ntt_round_plan(A, r, &nst, &wb, &lcur); r++) {
+    ntt_round_dispatch<F, INV>(f, smem, A, nst, wb, lcur, tid);
+    __syncthreads();
+  }
+  ntt_store_phase<F, MODE, INV>(f, smem, A, tile, tid, nthr);
+}
+
+// tab[i] = to_tw(w^i · s) for i < count  (plan building; w, s plain residues)
+template <class F>
+__global__ void pow_table_kernel(const F f, u64 w, u64 s, u64* tab, u32 count) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) tab[i] = f.to_tw(f.mul(field_pow(f, w, (u64)i), s));
+}
+#endif  // __CUDACC__
+
+}  // namespace ronk

@@ -1,0 +1,417 @@
+// poly.cu — Polynomial<Monomial|Lagrange, F, D> operations other than the transforms.
+// Mirrors src/polynomial/arithmetic.rs (Add :16-35, Sub :49-68, Mul :97-119, Div/Rem :121-146) and
+// src/polynomial/mod.rs (evaluate :133-139, quotient_and_remainder :170-225, dft :240-258,
+// Lagrange evaluate :382-415).
+#include "ntt_kernel.cuh"
+#include "ronk_internal.h"
+
+namespace ronk {
+
+// out[i] = a[i] ± (i < db ? b[i] : 0), i < da   (arithmetic.rs:23-34 / :56-67)
+template <class F, bool SUB>
+__global__ void poly_addsub_kernel(const F f, const u64* a, size_t da, const u64* b, size_t db, u64* out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < da; i += stride) {
+    const u64 y = (i < db) ? b[i] : 0ULL;
+    out[i] = SUB ? f.sub(a[i], y) : f.add(a[i], y);
+  }
+}
+
+// Schoolbook product (arithmetic.rs:110-118): one thread per output coefficient.
+template <class F>
+__global__ void poly_mul_schoolbook_kernel(const F f, const u64* a, size_t da, const u64* b, size_t db, u64* c) {
+  const size_t L = da + db - 1;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < L; k += stride) {
+    const size_t lo = (k >= db) ? k - db + 1 : 0, hi = (k < da) ? k : da - 1;
+    u64 acc = 0;
+    for (size_t i = lo; i <= hi; i++) acc = f.add(acc, f.mul(a[i], b[k - i]));
+    c[k] = acc;
+  }
+}
+
+// evaluate (mod.rs:133-139): out[pt] = Σ_j c_j x^j.  One CTA per point; thread t owns the
+// coefficients j ≡ t (mod 256) (coalesced), Horner in x^256, then a shared-memory tree sum.
+template <class F>
+__global__ void poly_eval_kernel(const F f, const u64* c, size_t d, const u64* xs, u64* out) {
+  __shared__ u64 red[256];
+  const u32 t = threadIdx.x;
+  const u64 x = xs[blockIdx.x];
+  const u64 y = field_pow(f, x, 256);
+  u64 acc = 0;
+  if (t < d) {
+    const size_t kmax = (d - 1 - t) / 256;
+    for (size_t k = kmax + 1; k-- > 0;) acc = f.add(f.mul(acc, y), c[t + 256 * k]);
+    acc = f.mul(acc, field_pow(f, x, (u64)t));
+  }
+  red[t] = acc;
+  __syncthreads();
+  for (u32 s = 128; s > 0; s >>= 1) {
+    if (t < s) red[t] = f.add(red[t], red[t + s]);
+    __syncthreads();
+  }
+  if (t == 0) out[blockIdx.x] = red[0];
+}
+
+// Lagrange-basis evaluate (mod.rs:382-415), literal fold semantics: the closure's early
+// `return c` replaces the accumulator, and l(x) multiplies the fold afterwards.
+template <class F>
+__global__ void lagrange_eval_kernel(const F f, const u64* c, const u64* nodes, u32 n, u64 x, u64* out, int* flag) {
+  __shared__ u64 red[256];
+  __shared__ u64 lred[256];
+  __shared__ u32 hit;  // index j* with nodes[j*] == x, or n
+  const u32 t = threadIdx.x;
+  if (t == 0) hit = n;
+  __syncthreads();
+  for (u32 j = t; j < n; j += blockDim.x)
+    if (nodes[j] == x) hit = j;
+  __syncthreads();
+  const u32 jstar = hit;
+  u64 acc = 0, lx = 1 % f.modulus();
+  for (u32 j = t; j < n; j += blockDim.x) {
+    lx = f.mul(lx, f.sub(x, nodes[j]));
+    if (jstar < n && j <= jstar) {
+      if (j == jstar) acc = f.add(acc, c[j]);
+      continue;
+    }
+    u64 wden = 1 % f.modulus();  // w_j^-1 = Π_{m≠j} (x_j - x_m)
+    for (u32 m = 0; m < n; m++)
+      if (m != j) wden = f.mul(wden, f.sub(nodes[j], nodes[m]));
+    const u64 den = f.mul(wden, f.sub(x, nodes[j]));
+    if (den == 0) { atomicExch(flag, 1); continue; }
+    acc = f.add(acc, f.mul(c[j], field_pow(f, den, f.modulus() - 2)));
+  }
+  red[t] = acc;
+  lred[t] = lx;
+  __syncthreads();
+  for (u32 s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (t < s) {
+      red[t] = f.add(red[t], red[t + s]);
+      lred[t] = f.mul(lred[t], lred[t + s]);
+    }
+    __syncthreads();
+  }
+  if (t == 0) out[0] = f.mul(lred[0], red[0]);
+}
+
+// quotient_and_remainder (mod.rs:170-225).  Single CTA; q and r have da terms.
+// flag: 1 = all-zero divisor / non-invertible, 2 = index out of range (the reference panics).
+template <class F>
+__global__ void poly_divrem_kernel(const F f, const u64* a, u32 da, const u64* b, u32 db, u64* q, u64* r, int* flag) {
+  __shared__ u32 s_deg, s_ok;
+  __shared__ u64 s_s;
+  const u32 t = threadIdx.x, nt = blockDim.x;
+  for (u32 i = t; i < da; i += nt) { q[i] = 0; r[i] = a[i]; }
+  __shared__ u32 s_rdeg, s_rfound;
+  if (t == 0) { s_rfound = 0; s_rdeg = 0; }
+  __syncthreads();
+  for (u32 i = t; i < db; i += nt)
+    if (b[i] != 0) { atomicMax(&s_rdeg, i); s_rfound = 1; }
+  __syncthreads();
+  const u32 rhs_degree = s_rdeg;
+  const bool rhs_nonzero = s_rfound != 0;
+  u64 cinv = 0;
+  if (rhs_nonzero) cinv = field_pow(f, b[rhs_degree], f.modulus() - 2);
+  u32 plen = da;  // p_coeffs.len() after trim_zeros
+  while (true) {
+    // find degree of the (trimmed) dividend: highest nonzero below plen
+    if (t == 0) { s_deg = 0; s_ok = 0; }
+    __syncthreads();
+    for (u32 i = t; i < plen; i += nt)
+      if (r[i] != 0) { atomicMax(&s_deg, i); s_ok = 1; }
+    __syncthreads();
+    const bool any = s_ok != 0;
+    const u32 p_degree = s_deg;
+    if (!(any && plen >= db)) break;                       // :183-184
+    if (!rhs_nonzero) { if (t == 0) atomicExch(flag, 1); break; }  // rposition().unwrap()
+    if (p_degree < rhs_degree) break;                      // :190-192
+    const u32 diff = p_degree - rhs_degree;
+    if (diff + db > plen) { if (t == 0) atomicExch(flag, 2); break; }  // p_coeffs[diff + i] out of range
+    __syncthreads();
+    if (t == 0) { s_s = f.mul(r[p_degree], cinv); q[diff] = s_s; }
+    __syncthreads();
+    const u64 s = s_s;
+    for (u32 i = t; i < db; i += nt) r[diff + i] = f.sub(r[diff + i], f.mul(b[i], s));
+    __syncthreads();
+    plen = p_degree;  // coefficient p_degree is now 0; trim_zeros continues below via the next scan
+    // trim_zeros pops every trailing zero: the next iteration's scan finds the new top, and
+    // plen must equal (new top + 1) for the `plen >= db` test.
+    if (t == 0) { s_deg = 0; s_ok = 0; }
+    __syncthreads();
+    for (u32 i = t; i < plen; i += nt)
+      if (r[i] != 0) { atomicMax(&s_deg, i); s_ok = 1; }
+    __syncthreads();
+    plen = s_ok ? s_deg + 1 : 0;
+    __syncthreads();
+  }
+}
+
+__global__ void pad_copy_kernel(u64* dst, const u64* src, size_t len, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (i < len) ? src[i] : 0ULL;
+}
+
+static int grid_for(ronk_ctx* ctx, size_t n, int threads) {
+  size_t blocks = (n + threads - 1) / threads;
+  size_t cap = (size_t)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  return (int)blocks;
+}
+
+template <class F>
+static int poly_mul_with_field(ronk_ctx* ctx, const F& f, u64 p, u64 g, const u64* a, size_t da, const u64* b,
+                               size_t db, u64* c) {
+  const size_t L = da + db - 1;
+  u32 log_n = 0;
+  while (((size_t)1 << log_n) < L) log_n++;
+  const bool ntt_ok = g != 0 && log_n >= 1 && log_n <= 28 && (p - 1) % ((u64)1 << log_n) == 0;
+  // NTT cost ~ 3·n·log n / 2 multiplies vs da·db for schoolbook
+  const double school = (double)da * (double)db;
+  const double viantt = 1.5 * (double)((size_t)1 << log_n) * (double)log_n + 4096.0;
+  if (!ntt_ok || school <= viantt) {
+    LaunchScope ls(ctx, "poly_mul_schoolbook");
+    poly_mul_schoolbook_kernel<F><<<grid_for(ctx, L, 128), 128, 0, ctx->stream>>>(f, a, da, b, db, c);
+    return check_launch(ctx, "poly_mul_schoolbook_kernel");
+  }
+  const size_t n = (size_t)1 << log_n;
+  RONK_TRY(ensure_ws(ctx, &ctx->ws2, &ctx->ws2_bytes, 2 * n * sizeof(u64)));
+  u64* A = (u64*)ctx->ws2;
+  u64* B = A + n;
+  {
+    LaunchScope ls(ctx, "pad_copy");
+    pad_copy_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(A, a, da, n);
+  }
+  {
+    LaunchScope ls(ctx, "pad_copy");
+    pad_copy_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(B, b, db, n);
+  }
+  RONK_TRY(check_launch(ctx, "pad_copy_kernel"));
+  RONK_TRY(ntt_device(ctx, p, g, A, nullptr, log_n, 1, 0));  // Â
+  RONK_TRY(ntt_device(ctx, p, g, B, A, log_n, 1, 0));        // B̂ ⊙ Â fused into the last stage
+  RONK_TRY(ntt_device(ctx, p, g, B, nullptr, log_n, 1, 1));  // back to coefficients
+  RONK_CUDA(ctx, cudaMemcpyAsync(c, B, L * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+  return RONK_OK;
+}
+
+static int poly_mul_device(ronk_ctx* ctx, u64 p, u64 g, const u64* a, size_t da, const u64* b, size_t db, u64* c) {
+  if (!ctx || !a || !b || !c) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (da == 0 || db == 0) return set_err(ctx, RONK_EINVAL, "empty polynomial (D + D2 - 1 underflows)");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (is_goldilocks_fast(p, g) || (p == GL_P && g == 0)) {
+    GoldilocksField f;
+    return poly_mul_with_field(ctx, f, p, g, a, da, b, db, c);
+  }
+  MontField f;
+  RONK_TRY(make_mont_field(ctx, p, 0, false, &f));
+  return poly_mul_with_field(ctx, f, p, g, a, da, b, db, c);
+}
+
+template <bool SUB>
+static int poly_addsub(ronk_ctx* ctx, u64 p, const u64* a, size_t da, const u64* b, size_t db, u64* out) {
+  if (!ctx || (da && (!a || !out)) || (db && !b)) return set_err(ctx, RONK_EINVAL, "null argument");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (da == 0) return RONK_OK;
+  const char* name = SUB ? "poly_sub" : "poly_add";
+  if (p == GL_P) {
+    GoldilocksField f;
+    LaunchScope ls(ctx, name);
+    poly_addsub_kernel<GoldilocksField, SUB><<<grid_for(ctx, da, 256), 256, 0, ctx->stream>>>(f, a, da, b, db, out);
+  } else {
+    MontField f;
+    RONK_TRY(make_mont_field(ctx, p, 0, false, &f));
+    LaunchScope ls(ctx, name);
+    poly_addsub_kernel<MontField, SUB><<<grid_for(ctx, da, 256), 256, 0, ctx->stream>>>(f, a, da, b, db, out);
+  }
+  return check_launch(ctx, name);
+}
+
+static int poly_eval_device(ronk_ctx* ctx, u64 p, const u64* c, size_t d, const u64* xs, size_t m, u64* out) {
+  if (!ctx || (m && (!xs || !out)) || (d && !c)) return set_err(ctx, RONK_EINVAL, "null argument");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (m == 0) return RONK_OK;
+  if (m > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "too many points");
+  if (p == GL_P) {
+    GoldilocksField f;
+    LaunchScope ls(ctx, "poly_eval");
+    poly_eval_kernel<GoldilocksField><<<(u32)m, 256, 0, ctx->stream>>>(f, c, d, xs, out);
+  } else {
+    MontField f;
+    RONK_TRY(make_mont_field(ctx, p, 0, false, &f));
+    LaunchScope ls(ctx, "poly_eval");
+    poly_eval_kernel<MontField><<<(u32)m, 256, 0, ctx->stream>>>(f, c, d, xs, out);
+  }
+  return check_launch(ctx, "poly_eval_kernel");
+}
+
+// nodes[i] = ω_n^i (plain residues)
+static int roots_table(ronk_ctx* ctx, u64 p, u64 g, u64 n, u64* nodes) {
+  u64 w;
+  if (ronk_root_of_unity(p, g, n, (uint64_t*)&w) != RONK_OK)
+    return set_err(ctx, RONK_EINVAL, "n must divide p - 1 (no primitive n-th root of unity)");
+  if (n > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "n too large");
+  // plain residues: use the Goldilocks policy's identity to_tw for GL, and for Mont build then
+  // convert back would be wasteful — a dedicated kernel keeps it simple.
+  if (p == GL_P) {
+    GoldilocksField f;
+    LaunchScope ls(ctx, "pow_table");
+    pow_table_kernel<GoldilocksField><<<((u32)n + 255) / 256, 256, 0, ctx->stream>>>(f, w, 1, nodes, (u32)n);
+  } else {
+    MontField f;
+    RONK_TRY(make_mont_field(ctx, p, 0, false, &f));
+    // to_tw(x) = x·R; passing s = R^-1 yields plain residues
+    const u64 r1 = (u64)((((unsigned __int128)1) << 64) % p);
+    const u64 rinv = h_powmod(r1, p - 2, p);
+    LaunchScope ls(ctx, "pow_table");
+    pow_table_kernel<MontField><<<((u32)n + 255) / 256, 256, 0, ctx->stream>>>(f, w, rinv, nodes, (u32)n);
+  }
+  return check_launch(ctx, "pow_table_kernel");
+}
+
+static int dft_device(ronk_ctx* ctx, u64 p, u64 g, const u64* in, u64 n, u64* out) {
+  if (!ctx || !in || !out) return set_err(ctx, RONK_EINVAL, "null argument");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (g == 0 || g >= p) return set_err(ctx, RONK_EINVAL, "generator out of range");
+  if (n == 0 || (p - 1) % n != 0)
+    return set_err(ctx, RONK_EINVAL, "n must divide p - 1 (no primitive n-th root of unity)");
+  RONK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, n * sizeof(u64)));
+  RONK_TRY(roots_table(ctx, p, g, n, (u64*)ctx->ws));
+  return poly_eval_device(ctx, p, in, n, (const u64*)ctx->ws, n, out);  // X[i] = a(ω^i)
+}
+
+}  // namespace ronk
+
+using namespace ronk;
+
+extern "C" {
+
+int ronk_poly_mul_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t* a, size_t da, const uint64_t* b,
+                      size_t db, uint64_t* c) {
+  return poly_mul_device(ctx, p, g, (const u64*)a, da, (const u64*)b, db, (u64*)c);
+}
+
+int ronk_poly_add_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, size_t da, const uint64_t* b, size_t db,
+                      uint64_t* out) {
+  return poly_addsub<false>(ctx, p, (const u64*)a, da, (const u64*)b, db, (u64*)out);
+}
+int ronk_poly_sub_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, size_t da, const uint64_t* b, size_t db,
+                      uint64_t* out) {
+  return poly_addsub<true>(ctx, p, (const u64*)a, da, (const u64*)b, db, (u64*)out);
+}
+
+int ronk_poly_eval_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* coeffs, size_t d, const uint64_t* xs, size_t m,
+                       uint64_t* out) {
+  return poly_eval_device(ctx, p, (const u64*)coeffs, d, (const u64*)xs, m, (u64*)out);
+}
+
+int ronk_dft_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t* in, uint64_t n, uint64_t* out) {
+  return dft_device(ctx, p, g, (const u64*)in, n, (u64*)out);
+}
+
+// ---- host-pointer variants ---------------------------------------------------------------------
+static int up(ronk_ctx* ctx, u64** d, const void* h, size_t n) {
+  RONK_CUDA(ctx, cudaMalloc((void**)d, (n ? n : 1) * sizeof(u64)));
+  if (n) RONK_CUDA(ctx, cudaMemcpyAsync(*d, h, n * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+  return RONK_OK;
+}
+static int down(ronk_ctx* ctx, void* h, const u64* d, size_t n) {
+  if (n) RONK_CUDA(ctx, cudaMemcpyAsync(h, d, n * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RONK_OK;
+}
+struct DevBuf {  // frees on scope exit
+  u64* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+int ronk_poly_mul_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t* a, size_t da, const uint64_t* b,
+                           size_t db, uint64_t* c) {
+  if (!ctx || !a || !b || !c) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (da == 0 || db == 0) return set_err(ctx, RONK_EINVAL, "empty polynomial (D + D2 - 1 underflows)");
+  DevBuf A, B, C;
+  RONK_TRY(up(ctx, &A.p, a, da));
+  RONK_TRY(up(ctx, &B.p, b, db));
+  RONK_CUDA(ctx, cudaMalloc((void**)&C.p, (da + db - 1) * sizeof(u64)));
+  RONK_TRY(poly_mul_device(ctx, p, g, A.p, da, B.p, db, C.p));
+  return down(ctx, c, C.p, da + db - 1);
+}
+
+int ronk_poly_eval_u64_host(ronk_ctx* ctx, uint64_t p, const uint64_t* coeffs, size_t d, const uint64_t* xs, size_t m,
+                            uint64_t* out) {
+  if (!ctx || (m && (!xs || !out)) || (d && !coeffs)) return set_err(ctx, RONK_EINVAL, "null argument");
+  DevBuf C, X, O;
+  RONK_TRY(up(ctx, &C.p, coeffs, d));
+  RONK_TRY(up(ctx, &X.p, xs, m));
+  RONK_CUDA(ctx, cudaMalloc((void**)&O.p, (m ? m : 1) * sizeof(u64)));
+  RONK_TRY(poly_eval_device(ctx, p, C.p, d, X.p, m, O.p));
+  return down(ctx, out, O.p, m);
+}
+
+int ronk_dft_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t* in, uint64_t n, uint64_t* out) {
+  if (!ctx || !in || !out) return set_err(ctx, RONK_EINVAL, "null argument");
+  DevBuf I, O;
+  RONK_TRY(up(ctx, &I.p, in, n));
+  RONK_CUDA(ctx, cudaMalloc((void**)&O.p, (n ? n : 1) * sizeof(u64)));
+  RONK_TRY(dft_device(ctx, p, g, I.p, n, O.p));
+  return down(ctx, out, O.p, n);
+}
+
+int ronk_poly_lagrange_eval_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t* coeffs, size_t n,
+                                     uint64_t x, uint64_t* out) {
+  if (!ctx || !coeffs || !out) return set_err(ctx, RONK_EINVAL, "null argument");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (g == 0 || g >= p || x >= p) return set_err(ctx, RONK_EINVAL, "argument out of range");
+  if (n == 0 || (p - 1) % n != 0)
+    return set_err(ctx, RONK_EINVAL, "n must divide p - 1 (Lagrange::new asserts)");  // mod.rs:361
+  if (n > (1u << 20)) return set_err(ctx, RONK_EUNSUPPORTED, "n too large for the O(n²) barycentric form");
+  DevBuf C, N, O;
+  RONK_TRY(up(ctx, &C.p, coeffs, n));
+  RONK_CUDA(ctx, cudaMalloc((void**)&N.p, n * sizeof(u64)));
+  RONK_CUDA(ctx, cudaMalloc((void**)&O.p, sizeof(u64)));
+  RONK_TRY(roots_table(ctx, p, g, n, N.p));
+  RONK_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+  if (p == GL_P) {
+    GoldilocksField f;
+    LaunchScope ls(ctx, "lagrange_eval");
+    lagrange_eval_kernel<GoldilocksField><<<1, 256, 0, ctx->stream>>>(f, C.p, N.p, (u32)n, x, O.p, ctx->d_flag);
+  } else {
+    MontField f;
+    RONK_TRY(make_mont_field(ctx, p, 0, false, &f));
+    LaunchScope ls(ctx, "lagrange_eval");
+    lagrange_eval_kernel<MontField><<<1, 256, 0, ctx->stream>>>(f, C.p, N.p, (u32)n, x, O.p, ctx->d_flag);
+  }
+  RONK_TRY(check_launch(ctx, "lagrange_eval_kernel"));
+  return down(ctx, out, O.p, 1);
+}
+
+int ronk_poly_divrem_u64_host(ronk_ctx* ctx, uint64_t p, const uint64_t* a, size_t da, const uint64_t* b, size_t db,
+                              uint64_t* q, uint64_t* r) {
+  if (!ctx || (da && (!a || !q || !r)) || (db && !b)) return set_err(ctx, RONK_EINVAL, "null argument");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (da > 0x7FFFFFF0ULL || db > 0x7FFFFFF0ULL) return set_err(ctx, RONK_EUNSUPPORTED, "polynomial too long");
+  if (da == 0) return RONK_OK;
+  DevBuf A, B, Qd, Rd;
+  RONK_TRY(up(ctx, &A.p, a, da));
+  RONK_TRY(up(ctx, &B.p, b, db));
+  RONK_CUDA(ctx, cudaMalloc((void**)&Qd.p, da * sizeof(u64)));
+  RONK_CUDA(ctx, cudaMalloc((void**)&Rd.p, da * sizeof(u64)));
+  RONK_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+  if (p == GL_P) {
+    GoldilocksField f;
+    LaunchScope ls(ctx, "poly_divrem");
+    poly_divrem_kernel<GoldilocksField><<<1, 256, 0, ctx->stream>>>(f, A.p, (u32)da, B.p, (u32)db, Qd.p, Rd.p, ctx->d_flag);
+  } else {
+    MontField f;
+    RONK_TRY(make_mont_field(ctx, p, 0, false, &f));
+    LaunchScope ls(ctx, "poly_divrem");
+    poly_divrem_kernel<MontField><<<1, 256, 0, ctx->stream>>>(f, A.p, (u32)da, B.p, (u32)db, Qd.p, Rd.p, ctx->d_flag);
+  }
+  RONK_TRY(check_launch(ctx, "poly_divrem_kernel"));
+  RONK_CUDA(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_CUDA(ctx, cudaMemcpyAsync(q, Qd.p, da * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_TRY(down(ctx, r, Rd.p, da));
+  if (*ctx->h_flag) return set_err(ctx, RONK_EINVAL, "polynomial division: the reference would panic on this divisor");
+  return RONK_OK;
+}
+
+}  // extern "C"

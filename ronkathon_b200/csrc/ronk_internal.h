@@ -1,0 +1,133 @@
+// ronk_internal.h — context object and launch helpers shared by the translation units of
+// libronk_b200.so.  Not part of the public ABI (include/ronk_b200.h is).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/ronk_b200.h"
+#include "field.cuh"
+
+namespace ronk {
+
+struct ProfRec {
+  char name[32];
+  cudaEvent_t start, stop;
+};
+
+struct NttPlan {
+  u64 p = 0, g = 0;
+  u32 log_n = 0;
+  bool two_pass = false;
+  u32 log_n1 = 0, log_n2 = 0;
+  u64* tw1 = nullptr;        // ω_{N1}^e (single pass: ω_n^e), twiddle form
+  u64* tw2 = nullptr;        // ω_{N2}^e == ω_n^(e·N1)
+  u64* tw_lo = nullptr;      // ω_n^x, x < N1
+  u64* tw_hi_inv = nullptr;  // ω_n^(y·N1) · n^-1
+  u64 scale_inv = 0;         // n^-1, twiddle form (single-pass inverse)
+};
+
+}  // namespace ronk
+
+struct ronk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  std::string err;
+  uint64_t launches = 0;
+  bool prof = false;
+  std::vector<ronk::ProfRec> prof_log;
+  std::map<std::tuple<uint64_t, uint64_t, uint32_t>, ronk::NttPlan> plans;
+  void* ws = nullptr;  // workspace (two-pass intermediate, poly_mul operands, msm partials)
+  size_t ws_bytes = 0;
+  void* ws2 = nullptr;  // second scratch buffer (poly_mul)
+  size_t ws2_bytes = 0;
+  int* d_flag = nullptr;  // device error flag
+  int* h_flag = nullptr;  // pinned host mirror
+};
+
+namespace ronk {
+
+inline int set_err(ronk_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define RONK_CUDA(ctx, expr)                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return ronk::set_err(ctx, _e == cudaErrorMemoryAllocation ? RONK_ENOMEM : RONK_ECUDA,   \
+                           std::string(#expr ": ") + cudaGetErrorString(_e));                 \
+  } while (0)
+
+#define RONK_TRY(expr)          \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != RONK_OK) return _rc; \
+  } while (0)
+
+// Brackets a kernel launch with the launch counter and (optionally) profiling events.
+struct LaunchScope {
+  ronk_ctx* ctx;
+  bool on;
+  cudaEvent_t start = nullptr, stop = nullptr;
+  const char* name;
+  LaunchScope(ronk_ctx* c, const char* n) : ctx(c), on(c->prof), name(n) {
+    ctx->launches++;
+    if (on) {
+      cudaEventCreate(&start);
+      cudaEventCreate(&stop);
+      cudaEventRecord(start, ctx->stream);
+    }
+  }
+  ~LaunchScope() {
+    if (on) {
+      cudaEventRecord(stop, ctx->stream);
+      ProfRec r;
+      std::memset(&r, 0, sizeof(r));
+      std::snprintf(r.name, sizeof(r.name), "%s", name);
+      r.start = start;
+      r.stop = stop;
+      ctx->prof_log.push_back(r);
+    }
+  }
+};
+
+inline int check_launch(ronk_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(ctx, RONK_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return RONK_OK;
+}
+
+inline int ensure_ws(ronk_ctx* ctx, void** buf, size_t* cap, size_t bytes) {
+  if (*cap >= bytes) return RONK_OK;
+  if (*buf) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+  }
+  cudaError_t e = cudaMalloc(buf, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_err(ctx, RONK_ENOMEM, "workspace allocation failed");
+  }
+  *cap = bytes;
+  return RONK_OK;
+}
+
+// Field policy construction (host).
+inline bool is_goldilocks_fast(u64 p, u64 g) { return p == GL_P && g == 7; }
+int make_mont_field(ronk_ctx* ctx, u64 p, u64 g, bool inverse, MontField* out);  // ntt.cu
+int validate_modulus(ronk_ctx* ctx, u64 p);                                       // field_ops.cu
+
+// Internal device-pointer entry points used across translation units.
+int ntt_device(ronk_ctx* ctx, u64 p, u64 g, u64* data, const u64* mul, u32 log_n, u32 batch, int inverse);
+
+}  // namespace ronk

@@ -1,0 +1,163 @@
+// ntt_emu.cpp — TEST INFRASTRUCTURE: compiles the product's kernel headers
+// (ronkathon_b200/csrc/field.cuh, ntt_kernel.cuh) for the host and executes the tile phases thread by
+// thread, so the CPU test tier can check the kernel's index maps, round schedule, twiddle tables and
+// field arithmetic against the oracle without a GPU.  Never linked into libronk_b200.so and never
+// used by the product path.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../ronkathon_b200/csrc/ntt_kernel.cuh"
+
+using namespace ronk;
+
+namespace {
+
+struct HostMont {
+  MontField f;
+};
+
+MontField make_mont(u64 p, u64 g, bool inverse) {  // mirrors make_mont_field() in ntt.cu
+  MontField f;
+  f.p = p;
+  f.pinv = h_inv64(p);
+  const u64 r1 = (u64)((((unsigned __int128)1) << 64) % p);
+  f.r2 = h_mulmod(r1, r1, p);
+  for (int e = 0; e < 8; e++) f.w16t[e] = r1;
+  if (g) {
+    u32 k = 0;
+    while (k < 4 && ((p - 1) >> k) % 2 == 0) k++;
+    if (k) {
+      u64 w = h_powmod(g, (p - 1) >> k, p);
+      if (inverse) w = h_powmod(w, ((u64)1 << k) - 1, p);
+      const int stride = 16 >> k;
+      for (int e = 0; e < 8; e++)
+        if (e % stride == 0) f.w16t[e] = h_mulmod(h_powmod(w, e / stride, p), r1, p);
+    }
+  }
+  return f;
+}
+
+template <class F>
+std::vector<u64> table(const F& f, u64 w, u64 s, u64 count) {  // pow_table_kernel
+  std::vector<u64> t(count);
+  for (u64 i = 0; i < count; i++) t[i] = f.to_tw(f.mul(field_pow(f, w, i), s));
+  return t;
+}
+
+template <class F, int MODE, bool INV>
+void run_tiles(const F& f, const NttTileArgs& A, u64 tiles) {
+  const u32 T = 1u << A.tile_log, nthr = T / 16;
+  std::vector<u64> smem(T);
+  for (u64 tile = 0; tile < tiles; tile++) {
+    for (u32 t = 0; t < nthr; t++) ntt_load_phase<F, MODE>(smem.data(), A, (u32)tile, t, nthr);
+    u32 nst, wb, lcur;
+    for (u32 r = 0; ntt_round_plan(A, r, &nst, &wb, &lcur); r++)
+      for (u32 t = 0; t < nthr; t++) ntt_round_dispatch<F, INV>(f, smem.data(), A, nst, wb, lcur, t);
+    for (u32 t = 0; t < nthr; t++) ntt_store_phase<F, MODE, INV>(f, smem.data(), A, (u32)tile, t, nthr);
+  }
+}
+
+template <class F, bool INV>
+int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 log_n, u32 batch, u32 tile_cap) {
+  const u64 n = (u64)1 << log_n;
+  const u64 w = h_powmod(g, (p - 1) / n, p);
+  const u64 ninv = h_powmod(n % p, p - 2, p);
+  const u64 scale = fast_gl ? ninv : h_mulmod(ninv, (u64)((((unsigned __int128)1) << 64) % p), p);
+  const NttShape sh = ntt_shape(log_n);
+  u64 tiles = 0;
+  if (!sh.two_pass) {
+    auto tw = table(f, w, 1, n);
+    NttTileArgs A = ntt_args_single(data, mul, tw.data(), scale, log_n, (u64)batch << log_n, INV, tile_cap, &tiles);
+    run_tiles<F, MODE_SINGLE, INV>(f, A, tiles);
+    return 0;
+  }
+  const u64 n1 = (u64)1 << sh.log_n1, n2 = (u64)1 << sh.log_n2;
+  auto tw1 = table(f, h_powmod(w, n2, p), 1, n1);
+  auto tw2 = table(f, h_powmod(w, n1, p), 1, n2);
+  auto tw_lo = table(f, w, 1, n1);
+  auto tw_hi_inv = table(f, h_powmod(w, n1, p), ninv, n2);
+  std::vector<u64> ws((size_t)batch << log_n);
+  NttTileArgs A1 =
+      ntt_args_pass1(data, ws.data(), tw1.data(), tw_lo.data(), INV ? tw_hi_inv.data() : tw2.data(), log_n, batch, &tiles);
+  run_tiles<F, MODE_PASS1, INV>(f, A1, tiles);
+  NttTileArgs A2 = ntt_args_pass2(ws.data(), data, mul, tw2.data(), log_n, batch, &tiles);
+  run_tiles<F, MODE_PASS2, INV>(f, A2, tiles);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Same contract as ronk_ntt_u64 / ronk_ntt_mul_u64, on host memory.
+int emu_ntt(uint64_t p, uint64_t g, uint64_t* data, const uint64_t* mul, uint32_t log_n, uint32_t batch, int inverse,
+            uint32_t tile_cap) {
+  if (log_n == 0 || log_n > 28 || (p - 1) % ((u64)1 << log_n) != 0) return 1;
+  if (p == GL_P && g == 7) {
+    GoldilocksField f;
+    return inverse ? run<GoldilocksField, true>(f, p, g, true, data, mul, log_n, batch, tile_cap)
+                   : run<GoldilocksField, false>(f, p, g, true, data, mul, log_n, batch, tile_cap);
+  }
+  MontField f = make_mont(p, g, inverse != 0);
+  return inverse ? run<MontField, true>(f, p, g, false, data, mul, log_n, batch, tile_cap)
+                 : run<MontField, false>(f, p, g, false, data, mul, log_n, batch, tile_cap);
+}
+
+// Field-policy arithmetic, element-wise, for cross-checks against the oracle.
+// op: 0 add, 1 sub, 2 mul, 3 neg(a), 4 a·2^b (Goldilocks only, b in the supported set)
+int emu_field_op(uint64_t p, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint64_t n, int force_mont) {
+  if (p == GL_P && !force_mont) {
+    GoldilocksField f;
+    for (u64 i = 0; i < n; i++) {
+      switch (op) {
+        case 0: out[i] = f.add(a[i], b[i]); break;
+        case 1: out[i] = f.sub(a[i], b[i]); break;
+        case 2: out[i] = f.mul(a[i], b[i]); break;
+        case 3: out[i] = f.neg(a[i]); break;
+        default: return 1;
+      }
+    }
+    return 0;
+  }
+  MontField f = make_mont(p, 0, false);
+  for (u64 i = 0; i < n; i++) {
+    switch (op) {
+      case 0: out[i] = f.add(a[i], b[i]); break;
+      case 1: out[i] = f.sub(a[i], b[i]); break;
+      case 2: out[i] = f.mul(a[i], b[i]); break;
+      case 3: out[i] = f.neg(a[i]); break;
+      default: return 1;
+    }
+  }
+  return 0;
+}
+
+// out[e] = a · ω16^e (e = 0..7) then a · ω16^-e (e = 0..7): the Goldilocks shift twiddles.
+void emu_gl_w16(uint64_t a, uint64_t out[16]) {
+  GoldilocksField f;
+  out[0] = f.w16<0, false>(a); out[1] = f.w16<1, false>(a); out[2] = f.w16<2, false>(a); out[3] = f.w16<3, false>(a);
+  out[4] = f.w16<4, false>(a); out[5] = f.w16<5, false>(a); out[6] = f.w16<6, false>(a); out[7] = f.w16<7, false>(a);
+  out[8] = f.w16<0, true>(a); out[9] = f.w16<1, true>(a); out[10] = f.w16<2, true>(a); out[11] = f.w16<3, true>(a);
+  out[12] = f.w16<4, true>(a); out[13] = f.w16<5, true>(a); out[14] = f.w16<6, true>(a); out[15] = f.w16<7, true>(a);
+}
+
+// Bank-conflict audit of the shared-memory swizzle: worst number of distinct 8-byte banks hit
+// twice by any half-warp in a window read at base bit `wb` for a tile of 2^tile_log elements.
+int emu_swizzle_worst_conflict(uint32_t tile_log, uint32_t wb) {
+  const u32 nthr = (1u << tile_log) / 16;
+  int worst = 1;
+  for (u32 hw = 0; hw < nthr / 16; hw++)
+    for (u32 q = 0; q < 16; q++) {
+      int cnt[16] = {0};
+      for (u32 l = 0; l < 16; l++) {
+        const u32 t = hw * 16 + l;
+        const u32 e0 = ((t >> wb) << (wb + 4)) | (t & ((1u << wb) - 1u));
+        cnt[swz(e0 | (q << wb)) & 15]++;
+      }
+      for (int k = 0; k < 16; k++) worst = cnt[k] > worst ? cnt[k] : worst;
+    }
+  return worst;
+}
+}

@@ -1,0 +1,173 @@
+"""GPU parity: Polynomial::fft / ifft / dft through the C ABI vs the reference KATs, the faithful
+oracle and the independent golden vectors.  Bit-exact everywhere (integer path)."""
+import numpy as np
+import pytest
+
+import oracle
+from gpu_util import GL, ctx, dev, host, summary
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_ntt(a, log_n, batch=1, inverse=False, p=GL, g=7):
+    from ronkathon_b200 import ops
+    d = dev(a)
+    ops.ntt_(ctx(), d, log_n, batch, inverse, p, g)
+    return host(d)
+
+
+def test_reference_kat_polynomial_api(kats):
+    """polynomial/tests.rs:119-142: dft == fft == [10,79,99,18]; ifft(fft(p)) == p."""
+    from ronkathon_b200 import PlutoBaseField, Polynomial, RonkPanic
+    ctx()
+    k = kats["polynomial"]
+    poly = Polynomial(k["a"], PlutoBaseField)
+    assert [int(v) for v in poly.fft().coefficients] == k["fft_a"]
+    assert [int(v) for v in poly.dft().coefficients] == k["dft_a"]
+    assert poly.fft().ifft() == poly
+    with pytest.raises(RonkPanic):                      # polynomial/tests.rs:46-55
+        Polynomial(k["dft_3_terms_panics"], PlutoBaseField).dft()
+    with pytest.raises(RonkPanic):                      # not a power of two (mod.rs:274)
+        Polynomial([1, 2, 3], PlutoBaseField).fft()
+    with pytest.raises(RonkPanic):                      # 8 ∤ 100: no 8th root of unity in F101
+        Polynomial([1] * 8, PlutoBaseField).fft()
+
+
+@pytest.mark.parametrize("p,log_n", [(101, 1), (101, 2), (17, 1), (17, 2), (17, 3), (17, 4), (127, 1)])
+def test_small_moduli_every_size(p, log_n):
+    g = oracle.generator(p)
+    n = 1 << log_n
+    rng = np.random.default_rng(log_n + p)
+    for batch in (1, 5, 1000):
+        a = rng.integers(0, p, n * batch).astype(np.uint64)
+        X = gpu_ntt(a, log_n, batch, p=p, g=g)
+        for b in (0, batch // 2, batch - 1):
+            assert np.array_equal(X[b * n:(b + 1) * n], oracle.fft(p, a[b * n:(b + 1) * n]))
+        assert np.array_equal(gpu_ntt(X, log_n, batch, True, p, g), a)
+
+
+@pytest.mark.parametrize("n", [2, 4, 5, 10, 20, 25, 50, 100])
+def test_dft_any_divisor_of_p_minus_1(n):
+    """dft works for every n | 100 over F101 (polynomial/mod.rs:240-258), not only powers of two."""
+    from ronkathon_b200 import PlutoBaseField, Polynomial
+    ctx()
+    a = list(np.random.default_rng(n).integers(0, 101, n))
+    assert [int(v) for v in Polynomial(a, PlutoBaseField).dft().coefficients] == list(oracle.dft(101, a))
+
+
+@pytest.mark.parametrize("log_n", list(range(1, 15)))
+def test_goldilocks_single_tile_sizes(log_n):
+    n = 1 << log_n
+    batch = 7 if log_n <= 11 else 2
+    a = oracle.splitmix(GL, 100 + log_n, n * batch)
+    X = gpu_ntt(a, log_n, batch)
+    for b in range(batch):
+        ref = oracle.fft(GL, a[b * n:(b + 1) * n]) if log_n <= 12 else oracle.ntt_fast(GL, a[b * n:(b + 1) * n])
+        assert np.array_equal(X[b * n:(b + 1) * n], ref), (log_n, b)
+    assert np.array_equal(gpu_ntt(X, log_n, batch, inverse=True), a)
+
+
+@pytest.mark.parametrize("log_n,batch", [(15, 3), (16, 2), (17, 1), (18, 2), (19, 1), (20, 1), (21, 1), (22, 1)])
+def test_goldilocks_two_pass_sizes(log_n, batch):
+    n = 1 << log_n
+    a = oracle.splitmix(GL, 42, n * batch)
+    X = gpu_ntt(a, log_n, batch)
+    for b in range(batch):
+        assert np.array_equal(X[b * n:(b + 1) * n], oracle.ntt_fast(GL, a[b * n:(b + 1) * n])), (log_n, b)
+    assert np.array_equal(gpu_ntt(X, log_n, batch, inverse=True), a)
+
+
+def test_generic_montgomery_path_on_goldilocks_and_other_64bit_primes():
+    """A different generator sends Goldilocks through the run-time-modulus Montgomery kernels —
+    the path p = 101 uses — and must agree with the oracle; so must another NTT-friendly prime."""
+    g5 = oracle.pow_(GL, 7, 5)
+    for log_n in (10, 16):
+        a = oracle.splitmix(GL, 5, 1 << log_n)
+        assert np.array_equal(gpu_ntt(a, log_n, g=g5), oracle.ntt_fast(GL, a, g=g5))
+    p2 = 4179340454199820289  # 29·2^57 + 1
+    g2 = 3
+    for log_n in (9, 13, 17):
+        a = oracle.splitmix(p2, 6, 1 << log_n)
+        X = gpu_ntt(a, log_n, p=p2, g=g2)
+        assert np.array_equal(X, oracle.ntt_fast(p2, a, g=g2))
+        assert np.array_equal(gpu_ntt(X, log_n, inverse=True, p=p2, g=g2), a)
+
+
+def test_golden_vectors(gold64):
+    """BASELINE config 2 (2^20 forward NTT, bit-exact vs CPU) + the independent pure-Python vectors."""
+    assert list(gpu_ntt(np.arange(1, 9, dtype=np.uint64), 3)) == gold64["ntt8_1to8"]
+    assert list(gpu_ntt(oracle.splitmix(GL, 42, 1024), 10)) == gold64["ntt_2_10_full"]
+    for lg in (16, 20):
+        X = gpu_ntt(oracle.splitmix(GL, 42, 1 << lg), lg)
+        g = gold64["ntt_2_%d" % lg]
+        s = summary(X)
+        for key in s:
+            assert s[key] == g[key], (lg, key)
+        for k, v in g["horner_checks"].items():
+            assert int(X[int(k)]) == v
+
+
+def test_metric_size_2_24_bit_exact_and_properties():
+    """The BASELINE metric size: 2^24 forward NTT, bit-exact vs the oracle, plus the
+    size-independent properties (round trip, linearity, spot X[k] == a(ω^k))."""
+    from ronkathon_b200 import ops
+    c = ctx()
+    lg, n = 24, 1 << 24
+    a = oracle.splitmix(GL, 42, n)
+    X = gpu_ntt(a, lg)
+    assert np.array_equal(X, oracle.ntt_fast(GL, a))
+    w = oracle.root_of_unity(GL, n)
+    for k in (0, 1, n // 2 + 3, n - 1):
+        assert int(X[k]) == oracle.poly_eval_horner(GL, a, oracle.pow_(GL, w, k))
+    assert np.array_equal(gpu_ntt(X, lg, inverse=True), a)
+    # linearity: NTT(a + b) == NTT(a) + NTT(b), all on the GPU
+    b = ops.splitmix_fill(c, n, 43)
+    da = dev(a)
+    s = ops.field_binop(c, "add", da, b)
+    ops.ntt_(c, s, lg); ops.ntt_(c, b, lg)
+    assert np.array_equal(host(s), host(ops.field_binop(c, "add", dev(X), b)))
+
+
+def test_fused_pointwise_multiply(gold64):
+    from ronkathon_b200 import ops
+    c = ctx()
+    for lg in (10, 16):
+        n = 1 << lg
+        a, b = oracle.splitmix(GL, 42, n), oracle.splitmix(GL, 43, n)
+        A, B = dev(a), dev(b)
+        ops.ntt_(c, A, lg)
+        ops.ntt_mul_(c, B, A, lg)
+        assert np.array_equal(host(B), oracle.vec_mul(GL, oracle.ntt_fast(GL, a), oracle.ntt_fast(GL, b)))
+        ops.ntt_(c, B, lg, inverse=True)
+        if lg == 16:
+            g = gold64["cyclic_conv_2_16_seed42_seed43"]
+            s = summary(host(B))
+            for key in s:
+                assert s[key] == g[key], key
+
+
+def test_batched_config5_shape():
+    """BASELINE config 5's per-GPU shard shape, reduced: 64 × 2^16 contiguous transforms."""
+    lg, batch = 16, 64
+    n = 1 << lg
+    a = oracle.splitmix(GL, 77, n * batch)
+    X = gpu_ntt(a, lg, batch)
+    for b in (0, 1, 31, 63):
+        assert np.array_equal(X[b * n:(b + 1) * n], oracle.ntt_fast(GL, a[b * n:(b + 1) * n]))
+    assert np.array_equal(gpu_ntt(X, lg, batch, inverse=True), a)
+
+
+def test_host_pointer_variant_and_errors():
+    from ronkathon_b200 import RonkError, RonkPanic
+    c = ctx()
+    a = oracle.splitmix(GL, 3, 1 << 13)
+    buf = a.copy()
+    c.call("ronk_ntt_u64_host", GL, 7, buf.ctypes.data, 13, 1, 0)
+    assert np.array_equal(buf, oracle.ntt_fast(GL, a))
+    with pytest.raises(RonkPanic):   # 2^33 ∤ p-1
+        c.call("ronk_ntt_u64", GL, 7, dev(a).data_ptr(), 33, 1, 0)
+    with pytest.raises(RonkError) as ei:
+        c.call("ronk_ntt_u64", GL, 7, dev(a).data_ptr(), 29, 1, 0)
+    assert ei.value.code == 5
+    with pytest.raises(RonkPanic):   # composite modulus
+        c.call("ronk_ntt_u64", 100, 7, dev(a).data_ptr(), 2, 1, 0)

@@ -1,0 +1,135 @@
+"""GPU parity: Polynomial arithmetic through the C ABI vs reference KATs / oracle
+(src/polynomial/arithmetic.rs tests, src/polynomial/tests.rs)."""
+import numpy as np
+import pytest
+
+import oracle
+from gpu_util import GL, ctx, dev, host
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_kats(kats):
+    from ronkathon_b200 import Lagrange, PlutoBaseField, Polynomial
+    ctx()
+    k = kats["polynomial"]
+    F = PlutoBaseField
+    P = lambda c: Polynomial(c, F)
+    a, b = P(k["a"]), P(k["b"])
+    a5 = Polynomial.from_array(k["a"], F, 5)
+    assert (b + a) == P(k["b_plus_a"])
+    assert (a5 - b) == P(k["a5_minus_b"])
+    assert (b - a5) == P(k["b_minus_a5"])
+    assert (-a) == P(k["neg_a"])
+    assert (a * b) == P(k["a_times_b"])
+    assert (P(k["c"]) * P(k["d"])) == P(k["c_times_d"])
+    assert (a / b) == P(k["a_div_b"]) and (a % b) == P(k["a_rem_b"])
+    assert (b / a) == P(k["b_div_a"]) and (b % a) == P(k["b_rem_a"])
+    assert (P([1, 2, 1]) / P([1, 1])) == P(k["p121_div_11"])
+    assert (P([1, 2, 1]) % P([1, 1])) == P(k["p121_rem_11"])
+    assert a.evaluate(F(2)) == F(k["eval_a_at_2"])
+    e = k["eval_103_at_0"]
+    assert P(e["coeffs"]).evaluate(F(e["x"])) == F(e["y"])
+    assert a.dft().evaluate(F(2)) == F(k["lagrange_eval_dft_a_at_2"])   # polynomial/tests.rs:35-44
+    assert a.degree() == k["degree_a"] and a.leading_coefficient() == F(k["leading_a"])
+    assert a.pow_mult(2, F(5)) == P(k["pow_mult_a_2_5"])
+    assert a.dft().basis is Lagrange
+    c1 = kats["config1_extra"]   # BASELINE config 1: degree-8 × degree-8 over F101
+    assert (P(c1["a"]) * P(c1["b"])) == P(c1["out"])
+
+
+def test_lagrange_evaluate_matches_oracle_including_node_quirk():
+    from ronkathon_b200 import Lagrange, PlutoBaseField, Polynomial
+    ctx()
+    rng = np.random.default_rng(3)
+    for n in (2, 4, 5, 10, 20):
+        c = [int(v) for v in rng.integers(0, 101, n)]
+        poly = Polynomial(c, PlutoBaseField, Lagrange)
+        for x in [0, 1, 2, 10, 57, 100]:
+            assert poly.evaluate(PlutoBaseField(x)).value == oracle.lagrange_eval(101, c, x), (n, x)
+
+
+def test_divrem_random_and_panics():
+    from ronkathon_b200 import PlutoBaseField, PlutoScalarField, Polynomial, RonkPanic
+    ctx()
+    rng = np.random.default_rng(4)
+    for F, p in ((PlutoBaseField, 101), (PlutoScalarField, 17)):
+        for da, db in ((9, 3), (6, 6), (12, 2), (4, 7), (40, 5)):
+            a = [int(v) for v in rng.integers(0, p, da)]
+            b = [int(v) for v in rng.integers(0, p, db)]
+            b[-1] = b[-1] or 1  # non-zero top coefficient (trailing zeros panic in the reference)
+            q, r = Polynomial(a, F).quotient_and_remainder(Polynomial(b, F))
+            eq, er = oracle.poly_divrem(p, a, b)
+            assert list(q.coefficients) == list(eq) and list(r.coefficients) == list(er)
+    with pytest.raises(RonkPanic):
+        Polynomial([1, 2, 3], PlutoBaseField) / Polynomial([0, 0], PlutoBaseField)
+    with pytest.raises(oracle.OraclePanic):
+        oracle.poly_divrem(101, [1, 2, 3], [0, 0])
+    # big field, long dividend
+    a, b = oracle.splitmix(GL, 1, 500), oracle.splitmix(GL, 2, 37)
+    from ronkathon_b200 import GoldilocksField
+    q, r = Polynomial(a, GoldilocksField).quotient_and_remainder(Polynomial(b, GoldilocksField))
+    eq, er = oracle.poly_divrem(GL, a, b)
+    assert np.array_equal(q.coefficients, eq) and np.array_equal(r.coefficients, er)
+
+
+def test_poly_mul_paths_vs_oracle(gold64):
+    from ronkathon_b200 import ops
+    c = ctx()
+    a3, b3 = oracle.splitmix(GL, 42, 300), oracle.splitmix(GL, 43, 300)
+    got = host(ops.poly_mul(c, dev(a3), dev(b3)))
+    assert list(got) == gold64["poly_mul_300x300_seed42_seed43"]
+    for da, db in ((1, 1), (1, 7), (2, 2), (33, 1), (64, 64), (1000, 3), (2000, 3000), (5000, 5000), (40000, 25000)):
+        a, b = oracle.splitmix(GL, da, da), oracle.splitmix(GL, db + 1, db)
+        got = host(ops.poly_mul(c, dev(a), dev(b)))
+        if da * db <= 4_000_000:
+            exp = oracle.poly_mul(GL, a, b)
+        else:  # convolution theorem with the oracle's transforms
+            L = da + db - 1
+            lg = (L - 1).bit_length()
+            pa, pb = np.zeros(1 << lg, np.uint64), np.zeros(1 << lg, np.uint64)
+            pa[:da], pb[:db] = a, b
+            exp = oracle.ntt_fast(GL, oracle.vec_mul(GL, oracle.ntt_fast(GL, pa), oracle.ntt_fast(GL, pb)), inverse=True)[:L]
+        assert np.array_equal(got, exp), (da, db)
+    # p = 101 cannot use a power-of-two NTT beyond n = 4: schoolbook kernel
+    rng = np.random.default_rng(9)
+    a, b = rng.integers(0, 101, 57).astype(np.uint64), rng.integers(0, 101, 91).astype(np.uint64)
+    assert np.array_equal(host(ops.poly_mul(c, dev(a), dev(b), p=101, g=2)), oracle.poly_mul(101, a, b))
+
+
+def test_config3_poly_mul_2_24():
+    """BASELINE config 3: two 2^23-coefficient polynomials (NTT + fused pointwise + iNTT, n = 2^24).
+    Checked bit-exactly against the oracle's convolution-theorem route, and through the
+    size-independent property c(x) == a(x)·b(x) at random points evaluated on the GPU."""
+    from ronkathon_b200 import ops
+    c = ctx()
+    d = 1 << 23
+    a, b = oracle.splitmix(GL, 42, d), oracle.splitmix(GL, 43, d)
+    A, B = dev(a), dev(b)
+    C = ops.poly_mul(c, A, B)
+    got = host(C)
+    assert len(got) == 2 * d - 1
+    n = 1 << 24
+    pa, pb = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    pa[:d], pb[:d] = a, b
+    exp = oracle.ntt_fast(GL, oracle.vec_mul(GL, oracle.ntt_fast(GL, pa), oracle.ntt_fast(GL, pb)), inverse=True)
+    assert exp[-1] == 0 and np.array_equal(got, exp[:-1])
+    xs = dev(oracle.splitmix(GL, 99, 4))
+    ea, eb, ec = host(ops.poly_eval(c, A, xs)), host(ops.poly_eval(c, B, xs)), host(ops.poly_eval(c, C, xs))
+    assert np.array_equal(ec, oracle.vec_mul(GL, ea, eb))
+
+
+def test_evaluate_vs_oracle(gold64):
+    from ronkathon_b200 import GoldilocksField, Polynomial, ops
+    c = ctx()
+    a3 = oracle.splitmix(GL, 42, 300)
+    e = gold64["eval_300_seed42_at_seed43_0"]
+    assert Polynomial(a3, GoldilocksField).evaluate(e["x"]).value == e["y"]
+    for d in (0, 1, 2, 255, 256, 257, 1000, 70000):
+        co = oracle.splitmix(GL, d + 5, d)
+        xs = np.concatenate([oracle.splitmix(GL, 8, 5), np.array([0, 1, GL - 1], dtype=np.uint64)])
+        got = host(ops.poly_eval(c, dev(co) if d else dev(np.zeros(1, np.uint64))[:0], dev(xs)))
+        exp = [oracle.poly_eval_horner(GL, co, int(x)) if d else 0 for x in xs]
+        assert list(got) == exp, d
+        if 0 < d <= 300:  # the reference's literal O(D²) form gives the same values
+            assert exp == [oracle.poly_eval(GL, co, int(x)) for x in xs]

@@ -1,0 +1,162 @@
+"""CPU emulation of the CUDA kernel logic (tests/emu/ntt_emu.cpp compiles the product's own
+field.cuh / ntt_kernel.cuh for the host and runs the tile phases thread by thread).  Checks index
+maps, round schedule, twiddle tables and field arithmetic against the oracle.  The emulator is
+test infrastructure; the product library never executes on the CPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GL = oracle.GOLDILOCKS
+P64 = C.POINTER(C.c_uint64)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = os.path.join(HERE, "emu", "ntt_emu.cpp")
+    so = os.path.join(HERE, "emu", "libntt_emu.so")
+    hdr = os.path.join(HERE, "..", "ronkathon_b200", "csrc", "ntt_kernel.cuh")
+    hdr2 = os.path.join(HERE, "..", "ronkathon_b200", "csrc", "field.cuh")
+    newest = max(os.path.getmtime(x) for x in (src, hdr, hdr2))
+    if not os.path.exists(so) or os.path.getmtime(so) < newest:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.emu_ntt.argtypes = [C.c_uint64, C.c_uint64, P64, P64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32]
+    lib.emu_field_op.argtypes = [C.c_uint64, C.c_int, P64, P64, P64, C.c_uint64, C.c_int]
+    lib.emu_gl_w16.argtypes = [C.c_uint64, P64]
+    lib.emu_swizzle_worst_conflict.argtypes = [C.c_uint32, C.c_uint32]
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(P64) if a is not None else None
+
+
+def emu_ntt(emu, p, g, data, log_n, batch=1, inverse=False, mul=None, tile_cap=12):
+    d = np.ascontiguousarray(data, dtype=np.uint64).copy()
+    m = None if mul is None else np.ascontiguousarray(mul, dtype=np.uint64)
+    rc = emu.emu_ntt(p, g, _ptr(d), _ptr(m), log_n, batch, int(inverse), tile_cap)
+    assert rc == 0
+    return d
+
+
+def edge_values(p):
+    vals = [0, 1, 2, p - 1, p - 2, p // 2, p // 2 + 1]
+    if p > (1 << 33):
+        vals += [(1 << 32) - 1, 1 << 32, (1 << 32) + 1, p - (1 << 32), p - (1 << 32) + 1, p - (1 << 32) - 1,
+                 (1 << 63), (1 << 63) + 1, 0xFFFFFFFF00000000, 0xFFFFFFFE00000002, 0x00000000FFFFFFFF]
+    return [v % p for v in vals]
+
+
+@pytest.mark.parametrize("p,force_mont", [(GL, 0), (GL, 1), (101, 0), (17, 0), (127, 0),
+                                          (0xFFFFFFFFFFFFFFC5, 0), (0x7FFFFFFFFFFFFFE7, 0), (4179340454199820289, 0)])
+def test_field_policies_match_oracle(emu, p, force_mont):
+    rng = np.random.default_rng(5)
+    ev = edge_values(p)
+    a = [x for x in ev for _ in ev] + [int(v) % p for v in rng.integers(0, 2**63, 4000, dtype=np.uint64) * 2 + 1]
+    b = [y for _ in ev for y in ev] + [int(v) % p for v in rng.integers(0, 2**63, 4000, dtype=np.uint64) * 2 + 1]
+    a, b = np.array(a, dtype=np.uint64), np.array(b, dtype=np.uint64)
+    out = np.empty_like(a)
+    for op, fn in ((0, oracle.add), (1, oracle.sub), (2, oracle.mul)):
+        assert emu.emu_field_op(p, op, _ptr(a), _ptr(b), _ptr(out), len(a), force_mont) == 0
+        exp = np.array([fn(p, int(x), int(y)) for x, y in zip(a, b)], dtype=np.uint64)
+        assert np.array_equal(out, exp), op
+    assert emu.emu_field_op(p, 3, _ptr(a), _ptr(b), _ptr(out), len(a), force_mont) == 0
+    assert np.array_equal(out, np.array([oracle.neg(p, int(x)) for x in a], dtype=np.uint64))
+
+
+def test_goldilocks_shift_twiddles(emu):
+    w16 = oracle.root_of_unity(GL, 16)
+    w16i = oracle.inverse(GL, w16)
+    out = np.empty(16, dtype=np.uint64)
+    for a in edge_values(GL) + [int(v) for v in oracle.splitmix(GL, 9, 50)]:
+        emu.emu_gl_w16(a, _ptr(out))
+        for e in range(8):
+            assert int(out[e]) == oracle.mul(GL, a, oracle.pow_(GL, w16, e)), (a, e)
+            assert int(out[8 + e]) == oracle.mul(GL, a, oracle.pow_(GL, w16i, e)), (a, e)
+
+
+def test_swizzle_is_conflict_free(emu):
+    for tile_log in (9, 10, 12, 14):
+        for wb in range(0, tile_log - 3):
+            assert emu.emu_swizzle_worst_conflict(tile_log, wb) == 1, (tile_log, wb)
+
+
+@pytest.mark.parametrize("p,log_n", [(101, 1), (101, 2), (17, 1), (17, 2), (17, 3), (17, 4), (127, 1)])
+def test_emulated_small_moduli_match_reference_fft(emu, p, log_n):
+    g = oracle.generator(p)
+    n = 1 << log_n
+    rng = np.random.default_rng(log_n)
+    for batch in (1, 3, 37):
+        a = rng.integers(0, p, n * batch).astype(np.uint64)
+        X = emu_ntt(emu, p, g, a, log_n, batch)
+        for b in range(batch):
+            assert np.array_equal(X[b * n:(b + 1) * n], oracle.fft(p, a[b * n:(b + 1) * n]))
+        back = emu_ntt(emu, p, g, X, log_n, batch, inverse=True)
+        assert np.array_equal(back, a)
+        for b in range(batch):
+            assert np.array_equal(back[b * n:(b + 1) * n], oracle.ifft(p, X[b * n:(b + 1) * n]))
+
+
+def test_emulated_reference_kat(emu, kats):
+    k = kats["polynomial"]
+    X = emu_ntt(emu, 101, 2, k["a"], 2)
+    assert list(X) == k["fft_a"]
+    assert list(emu_ntt(emu, 101, 2, X, 2, inverse=True)) == k["a"]
+
+
+@pytest.mark.parametrize("log_n", list(range(1, 15)))
+@pytest.mark.parametrize("mont", [False, True])
+def test_emulated_goldilocks_single_pass(emu, log_n, mont):
+    n = 1 << log_n
+    g = 7
+    p = GL
+    if mont:  # a different generator routes Goldilocks through the generic Montgomery policy
+        g = oracle.pow_(GL, 7, 5)
+    batch = 3 if log_n <= 12 else 1
+    a = oracle.splitmix(p, 100 + log_n, n * batch)
+    X = emu_ntt(emu, p, g, a, log_n, batch)
+    for b in range(batch):
+        assert np.array_equal(X[b * n:(b + 1) * n], oracle.ntt_fast(p, a[b * n:(b + 1) * n], g=g)), b
+    assert np.array_equal(emu_ntt(emu, p, g, X, log_n, batch, inverse=True), a)
+
+
+def test_emulated_golden_vectors(emu, gold64):
+    assert list(emu_ntt(emu, GL, 7, list(range(1, 9)), 3)) == gold64["ntt8_1to8"]
+    a = oracle.splitmix(GL, 42, 1024)
+    assert list(emu_ntt(emu, GL, 7, a, 10)) == gold64["ntt_2_10_full"]
+
+
+@pytest.mark.parametrize("log_n,batch", [(15, 1), (16, 2), (17, 1), (18, 1)])
+def test_emulated_goldilocks_two_pass(emu, log_n, batch):
+    n = 1 << log_n
+    a = oracle.splitmix(GL, 42, n * batch)
+    X = emu_ntt(emu, GL, 7, a, log_n, batch)
+    for b in range(batch):
+        assert np.array_equal(X[b * n:(b + 1) * n], oracle.ntt_fast(GL, a[b * n:(b + 1) * n]))
+    assert np.array_equal(emu_ntt(emu, GL, 7, X, log_n, batch, inverse=True), a)
+
+
+def test_emulated_two_pass_generic_and_fused_mul(emu, gold64):
+    log_n, n = 16, 1 << 16
+    a, b = oracle.splitmix(GL, 42, n), oracle.splitmix(GL, 43, n)
+    g5 = oracle.pow_(GL, 7, 5)
+    assert np.array_equal(emu_ntt(emu, GL, g5, a, log_n), oracle.ntt_fast(GL, a, g=g5))
+    # fused point-wise multiply in the last stage, then inverse: the cyclic convolution golden
+    A = emu_ntt(emu, GL, 7, a, log_n)
+    AB = emu_ntt(emu, GL, 7, b, log_n, mul=A)
+    c = emu_ntt(emu, GL, 7, AB, log_n, inverse=True)
+    gsum = gold64["cyclic_conv_2_16_seed42_seed43"]
+    assert int(c[0]) == gsum["first"] and int(c[1]) == gsum["second"] and int(c[-1]) == gsum["last"]
+    assert int(np.sum(c, dtype=np.uint64)) == gsum["sum_mod_2_64"]
+    assert int(np.bitwise_xor.reduce(c)) == gsum["xor"]
+    # single-pass fused multiply
+    a10, b10 = a[:1024].copy(), b[:1024].copy()
+    A10 = emu_ntt(emu, GL, 7, a10, 10)
+    exp = np.array([oracle.mul(GL, int(x), int(y)) for x, y in zip(oracle.ntt_fast(GL, b10), A10)], dtype=np.uint64)
+    assert np.array_equal(emu_ntt(emu, GL, 7, b10, 10, mul=A10), exp)
