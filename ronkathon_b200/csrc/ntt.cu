@@ -129,9 +129,9 @@ int ntt_device(ronk_ctx* ctx, u64 p, u64 g, u64* data, const u64* mul, u32 log_n
   if (!ctx || !data) return set_err(ctx, RONK_EINVAL, "null argument");
   RONK_TRY(validate_modulus(ctx, p));
   if (g == 0 || g >= p) return set_err(ctx, RONK_EINVAL, "generator out of range");
-  if (log_n > 28) return set_err(ctx, RONK_EUNSUPPORTED, "log_n > 28 not supported");
   if (log_n >= 64 || (p - 1) % ((u64)1 << log_n) != 0)
     return set_err(ctx, RONK_EINVAL, "n must divide p - 1 (no primitive n-th root of unity)");
+  if (log_n > 28) return set_err(ctx, RONK_EUNSUPPORTED, "log_n > 28 not supported");
   if (batch == 0) return RONK_OK;
   if (log_n == 0) {
     if (mul) return ronk_field_mul_u64(ctx, p, (const uint64_t*)data, (const uint64_t*)mul, (uint64_t*)data, batch);
