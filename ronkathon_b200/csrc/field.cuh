@@ -44,35 +44,129 @@ constexpr u64 GL_EPS = 0xFFFFFFFFULL;  // 2^64 mod p
 struct GoldilocksField {
   RONK_HD u64 modulus() const { return GL_P; }
 
-  // (a + b) mod p, canonical in → canonical out.
+#if defined(__CUDA_ARCH__)
+  // ---- device path: explicit carry chains (inline PTX).  All values canonical in and out. ----
+  // Canonical by construction — no compare/select anywhere:
+  //   sub: a - b, borrow → +p (≡ -EPS mod 2^64); a, b < p ⇒ result in [0, p).
+  //   add: a + b = a - (p - b); p - b ∈ [1, p] and sub(a, p) = a still holds (borrow path).
+  static __device__ __forceinline__ u64 sub_words(u32 a0, u32 a1, u32 b0, u32 b1) {
+    u32 d0, d1;
+    asm("{\n\t.reg .u32 m;\n\t"
+        "sub.cc.u32 %0, %2, %4;\n\t"
+        "subc.cc.u32 %1, %3, %5;\n\t"
+        "subc.u32 m, 0, 0;\n\t"        // m = -borrow = EPS·borrow
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(d0), "=&r"(d1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return ((u64)d1 << 32) | d0;
+  }
+  __device__ __forceinline__ u64 sub(u64 a, u64 b) const {
+    return sub_words((u32)a, (u32)(a >> 32), (u32)b, (u32)(b >> 32));
+  }
+  __device__ __forceinline__ u64 add(u64 a, u64 b) const {
+    u32 n0, n1;
+    asm("sub.cc.u32 %0, 1, %2;\n\t"
+        "subc.u32 %1, 0xFFFFFFFF, %3;"
+        : "=&r"(n0), "=&r"(n1)
+        : "r"((u32)b), "r"((u32)(b >> 32)));   // (n1:n0) = p - b
+    return sub_words((u32)a, (u32)(a >> 32), n0, n1);
+  }
+  __device__ __forceinline__ u64 neg(u64 a) const { return a ? GL_P - a : 0; }
+
+  // words r0 + r1·B + r2·B² + r3·B³ (B = 2^32; B² ≡ B-1, B³ ≡ -1) → canonical residue:
+  //   Y = r2·EPS + r0 (one IMAD.WIDE, ≤ p-1), W = r1·B ≤ p-1, so
+  //   x = (Y - r3) + W = sub(sub(Y, r3), p - W) with p - W = (~r1 : 1) — two canonical subs.
+  static __device__ __forceinline__ u64 reduce_words(u32 r0, u32 r1, u32 r2, u32 r3) {
+    u32 z0, z1;
+    asm("{\n\t.reg .u64 y;\n\t.reg .u32 y0, y1, m, n1;\n\t"
+        "mad.wide.u32 y, %4, 0xFFFFFFFF, %6;\n\t"
+        "mov.b64 {y0, y1}, y;\n\t"
+        "sub.cc.u32 %0, y0, %5;\n\t"        // Y - r3
+        "subc.cc.u32 %1, y1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t"
+        "not.b32 n1, %3;\n\t"               // p - W = (~r1 : 1)
+        "sub.cc.u32 %0, %0, 1;\n\t"
+        "subc.cc.u32 %1, %1, n1;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(z0), "=&r"(z1)
+        : "r"(r0), "r"(r1), "r"(r2), "r"(r3), "l"((u64)r0));
+    return ((u64)z1 << 32) | z0;
+  }
+  __device__ __forceinline__ u64 reduce128(u64 lo, u64 hi) const {
+    return reduce_words((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
+  }
+  __device__ __forceinline__ u64 mul(u64 a, u64 b) const {
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    u32 r0, r1, r2, r3;
+    asm("{\n\t.reg .u64 t, u, v, z;\n\t.reg .u32 t1, u0, u1, v1;\n\t"
+        "mul.wide.u32 t, %4, %6;\n\t"            // a0·b0
+        "mov.b64 {%0, t1}, t;\n\t"
+        "cvt.u64.u32 u, t1;\n\t"
+        "mad.wide.u32 u, %4, %7, u;\n\t"         // a0·b1 + t1        (no overflow)
+        "mov.b64 {u0, u1}, u;\n\t"
+        "cvt.u64.u32 v, u0;\n\t"
+        "mad.wide.u32 v, %5, %6, v;\n\t"         // a1·b0 + u0        (no overflow)
+        "mov.b64 {%1, v1}, v;\n\t"
+        "cvt.u64.u32 z, u1;\n\t"
+        "mad.wide.u32 z, %5, %7, z;\n\t"         // a1·b1 + u1
+        "cvt.u64.u32 t, v1;\n\t"
+        "add.u64 z, z, t;\n\t"                   // + v1               (< 2^64: product < 2^128)
+        "mov.b64 {%2, %3}, z;\n\t}"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return reduce_words(r0, r1, r2, r3);
+  }
+  // a · 2^S for a compile-time S in [0, 192), on 32-bit words (2^96 ≡ -1).
+  template <int S>
+  __device__ __forceinline__ u64 mul_pow2(u64 a) const {
+    static_assert(S >= 0 && S < 192, "shift out of range");
+    if constexpr (S == 0) {
+      return a;
+    } else if constexpr (S >= 96) {
+      return neg(mul_pow2<S - 96>(a));
+    } else {
+      const u32 a0 = (u32)a, a1 = (u32)(a >> 32);
+      constexpr int s = S % 32;
+      // (y2:y1:y0) = a << s  (96 bits)
+      const u32 y0 = a0 << s;
+      const u32 y1 = s ? __funnelshift_l(a0, a1, s) : a1;
+      const u32 y2 = s ? (a1 >> (32 - s)) : 0u;
+      if constexpr (S < 32) return reduce_words(y0, y1, y2, 0u);
+      else if constexpr (S < 64) return reduce_words(0u, y0, y1, y2);
+      else {
+        // y·B² = y0·B² + y1·B³ + y2·B⁴ ≡ y0·EPS - (y2:y1);  y0·EPS < p and (y2:y1) < 2^63 < p
+        const u64 yy = (u64)y0 * 0xFFFFFFFFull;
+        return sub(yy, ((u64)y2 << 32) | y1);
+      }
+    }
+  }
+#else
+  // ---- host path (tests/emu only): portable C with identical results ----
   RONK_DEV u64 add(u64 a, u64 b) const {
     u64 s = a + b;
-    // s wrapped (carry) or s >= p  ⇔  a + b >= p  (a, b < p): subtract p == add EPS mod 2^64
     u64 t = s + GL_EPS;
     return (s < a || t < s) ? t : s;
   }
-  // (a - b) mod p: borrow → add p back (== subtract EPS mod 2^64)
   RONK_DEV u64 sub(u64 a, u64 b) const {
     u64 d = a - b;
     return (a < b) ? d - GL_EPS : d;
   }
   RONK_DEV u64 neg(u64 a) const { return a ? GL_P - a : 0; }
-
-  // 128-bit (hi:lo) → canonical residue.  x = lo + hi_lo·2^64 + hi_hi·2^96 ≡ lo + hi_lo·EPS - hi_hi.
   RONK_DEV u64 reduce128(u64 lo, u64 hi) const {
     u64 hh = hi >> 32, hl = hi & 0xFFFFFFFFULL;
     u64 t0 = lo - hh;
-    if (lo < hh) t0 -= GL_EPS;          // wrapped: +p
-    u64 t1 = (hl << 32) - hl;           // hl·EPS < 2^64
+    if (lo < hh) t0 -= GL_EPS;
+    u64 t1 = (hl << 32) - hl;
     u64 r = t0 + t1;
-    if (r < t1) r += GL_EPS;            // wrapped: 2^64 ≡ EPS, cannot wrap twice
+    if (r < t1) r += GL_EPS;
     return (r >= GL_P) ? r - GL_P : r;
   }
   RONK_DEV u64 mul(u64 a, u64 b) const { return reduce128(a * b, mulhi64(a, b)); }
-  RONK_DEV u64 mul_tw(u64 a, u64 w) const { return mul(a, w); }
-  RONK_DEV u64 to_tw(u64 w) const { return w; }
-
-  // a · 2^S mod p for a compile-time S in [0, 192)  (2 has order 192: 2^96 ≡ -1).
   template <int S>
   RONK_DEV u64 mul_pow2(u64 a) const {
     static_assert(S >= 0 && S < 192, "shift out of range");
@@ -86,6 +180,10 @@ struct GoldilocksField {
       return mul_pow2<S - 32>(mul_pow2<32>(a));
     }
   }
+#endif
+  RONK_DEV u64 mul_tw(u64 a, u64 w) const { return mul(a, w); }
+  RONK_DEV u64 to_tw(u64 w) const { return w; }
+
   // a · ω16^E (forward) or a · ω16^-E (INV), E in [0,8).  ω16 = g^((p-1)/16) = 2^156 for g = 7.
   template <int E, bool INV>
   RONK_DEV u64 w16(u64 a) const {

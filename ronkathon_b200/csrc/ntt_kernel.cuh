@@ -101,9 +101,21 @@ template <int NST, bool INV, class F>
 RONK_DEV void ntt_round(const F& f, u64* smem, const NttTileArgs& A, u32 wb, u32 lcur, u32 t) {
   const u32 lowmask = (1u << wb) - 1u;
   const u32 e0 = ((t >> wb) << (wb + 4)) | (t & lowmask);
+  // The swizzle is XOR-linear and e0 has no bits inside the window, so the 16 addresses are
+  // swz(e0) ^ swz(q << wb): walk q in Gray-code order and pay one XOR per access.
+  const u32 base = swz(e0);
+  const u32 g0 = swz(1u << wb), g1 = swz(2u << wb), g2 = swz(4u << wb), g3 = swz(8u << wb);
   u64 x[16];
+  {
+    u32 addr = base;
 #pragma unroll
-  for (int q = 0; q < 16; q++) x[q] = smem[swz(e0 | ((u32)q << wb))];
+    for (int i = 0; i < 16; i++) {
+      const int q = i ^ (i >> 1);
+      x[q] = smem[addr];
+      const int flip = (i + 1) & -(i + 1);  // Gray code: bit index = ctz(i + 1)
+      addr ^= (flip == 1) ? g0 : (flip == 2) ? g1 : (flip == 4) ? g2 : (flip == 8) ? g3 : 0u;
+    }
+  }
   radix_network<NST, INV>(f, x);
   if (NST == 4 && lcur > 4) {
     const u32 M1 = (1u << A.log_m) - 1u;
@@ -117,8 +129,16 @@ RONK_DEV void ntt_round(const F& f, u64* smem, const NttTileArgs& A, u32 wb, u32
       x[j] = f.mul_tw(x[j], ld_tw(A.tw_tile + idx));
     }
   }
+  {
+    u32 addr = base;
 #pragma unroll
-  for (int q = 0; q < 16; q++) smem[swz(e0 | ((u32)q << wb))] = x[q];
+    for (int i = 0; i < 16; i++) {
+      const int q = i ^ (i >> 1);
+      smem[addr] = x[q];
+      const int flip = (i + 1) & -(i + 1);
+      addr ^= (flip == 1) ? g0 : (flip == 2) ? g1 : (flip == 4) ? g2 : (flip == 8) ? g3 : 0u;
+    }
+  }
 }
 
 // ---------------- load phase: HBM → shared ----------------
