@@ -96,7 +96,7 @@ int ronk_field_pow_u64_host(ronk_ctx *ctx, uint64_t p, const uint64_t *a, uint64
 /* Polynomial::fft / ifft — src/polynomial/mod.rs:273-323 / :430-484.  In place, `batch`
  * contiguous transforms of 2^log_n points, NATURAL order in and out, X[k] = Σ_j a_j ω^(jk),
  * ω = g^((p-1)/2^log_n); inverse uses ω^-1 and scales by (2^log_n)^-1.
- * RONK_EINVAL if 2^log_n does not divide p-1; RONK_EUNSUPPORTED if log_n > 24. */
+ * RONK_EINVAL if 2^log_n does not divide p-1; RONK_EUNSUPPORTED if log_n > 26. */
 int ronk_ntt_u64(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *data, uint32_t log_n, uint32_t batch, int inverse);
 int ronk_ntt_u64_host(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *host_data, uint32_t log_n, uint32_t batch, int inverse);
 /* Forward transform whose last stage also multiplies point-wise by `mul` (same shape, natural

@@ -191,6 +191,14 @@ struct GoldilocksField {
     constexpr int sh = INV ? (192 - fwd) % 192 : fwd;
     return mul_pow2<sh>(a);
   }
+  // (a - b) · ω16^±E: a shift of 96+s is -2^s, so the sign is folded into the subtraction for free.
+  template <int E, bool INV>
+  RONK_DEV u64 w16_sub(u64 a, u64 b) const {
+    constexpr int fwd = (156 * E) % 192;
+    constexpr int sh = INV ? (192 - fwd) % 192 : fwd;
+    if constexpr (sh >= 96) return mul_pow2<sh - 96>(sub(b, a));
+    else return mul_pow2<sh>(sub(a, b));
+  }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -228,6 +236,10 @@ struct MontField {
   RONK_DEV u64 w16(u64 a) const {
     if constexpr (E == 0) return a;
     return redc_mul(a, w16t[E]);
+  }
+  template <int E, bool INV>
+  RONK_DEV u64 w16_sub(u64 a, u64 b) const {
+    return w16<E, INV>(sub(a, b));
   }
 };
 

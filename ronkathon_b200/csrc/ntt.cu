@@ -69,21 +69,36 @@ static int build_plan(ronk_ctx* ctx, const F& f, u64 p, u64 g, u32 log_n, NttPla
   return RONK_OK;
 }
 
-template <class F, int MODE, bool INV>
-static int launch_tile(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
-  const u32 T = 1u << A.tile_log;
-  const size_t smem = (size_t)T * sizeof(u64);
+template <class F, int MODE, bool INV, int NTHR>
+static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
+  const size_t smem = ((size_t)1 << A.tile_log) * sizeof(u64) + ((size_t)1 << A.log_m) * sizeof(u64) + 16;
   static bool attr_done = false;  // one device per process in practice; re-set is harmless
-  if (!attr_done || smem > 48 * 1024) {
-    RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_tile_kernel<F, MODE, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        128 * 1024));
+  if (!attr_done) {
+    RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_tile_kernel<F, MODE, INV, NTHR>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_done = true;
   }
   {
     LaunchScope ls(ctx, name);
-    ntt_tile_kernel<F, MODE, INV><<<tiles, T / 16, smem, ctx->stream>>>(f, A);
+    ntt_tile_kernel<F, MODE, INV, NTHR><<<tiles, NTHR, smem, ctx->stream>>>(f, A);
   }
   return check_launch(ctx, name);
+}
+
+// CTA size: one thread per 16 tile elements up to 512 threads (128 registers each, no spills);
+// RONK_NTT_THREADS=1024 selects the 64-register variant for experiments.
+template <class F, int MODE, bool INV>
+static int launch_tile(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
+  const u32 groups = (1u << A.tile_log) / 16;
+  static int pref = 0;
+  if (!pref) {
+    const char* s = getenv("RONK_NTT_THREADS");
+    pref = s ? atoi(s) : 512;
+  }
+  if (groups >= 1024 && pref >= 1024) return launch_tile_n<F, MODE, INV, 1024>(ctx, f, A, tiles, name);
+  if (groups >= 512) return launch_tile_n<F, MODE, INV, 512>(ctx, f, A, tiles, name);
+  if (groups >= 128) return launch_tile_n<F, MODE, INV, 128>(ctx, f, A, tiles, name);
+  return launch_tile_n<F, MODE, INV, 32>(ctx, f, A, tiles, name);
 }
 
 template <class F, bool INV>
@@ -131,7 +146,7 @@ int ntt_device(ronk_ctx* ctx, u64 p, u64 g, u64* data, const u64* mul, u32 log_n
   if (g == 0 || g >= p) return set_err(ctx, RONK_EINVAL, "generator out of range");
   if (log_n >= 64 || (p - 1) % ((u64)1 << log_n) != 0)
     return set_err(ctx, RONK_EINVAL, "n must divide p - 1 (no primitive n-th root of unity)");
-  if (log_n > 28) return set_err(ctx, RONK_EUNSUPPORTED, "log_n > 28 not supported");
+  if (log_n > 26) return set_err(ctx, RONK_EUNSUPPORTED, "log_n > 26 not supported");
   if (batch == 0) return RONK_OK;
   if (log_n == 0) {
     if (mul) return ronk_field_mul_u64(ctx, p, (const uint64_t*)data, (const uint64_t*)mul, (uint64_t*)data, batch);
@@ -164,7 +179,7 @@ extern "C" int ronk_ntt_mul_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t*
 extern "C" int ronk_ntt_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* host_data, uint32_t log_n,
                                  uint32_t batch, int inverse) {
   if (!ctx || !host_data) return set_err(ctx, RONK_EINVAL, "null argument");
-  if (log_n > 28) return set_err(ctx, RONK_EUNSUPPORTED, "log_n > 28 not supported");
+  if (log_n > 26) return set_err(ctx, RONK_EUNSUPPORTED, "log_n > 26 not supported");
   const size_t bytes = ((size_t)batch << log_n) * sizeof(u64);
   if (bytes == 0) return RONK_OK;
   RONK_TRY(ensure_ws(ctx, &ctx->ws2, &ctx->ws2_bytes, bytes));

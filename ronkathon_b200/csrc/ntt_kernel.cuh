@@ -78,7 +78,7 @@ RONK_DEV void bf_one(const F& f, u64 (&x)[16]) {
   if constexpr ((Q & h) == 0) {
     u64 a = x[Q], b = x[Q + h];
     x[Q] = f.add(a, b);
-    x[Q + h] = f.template w16<(Q & (h - 1)) * (8 / h), INV>(f.sub(a, b));
+    x[Q + h] = f.template w16_sub<(Q & (h - 1)) * (8 / h), INV>(a, b);
   }
 }
 template <int BETA, bool INV, class F, int... Q>
@@ -98,7 +98,7 @@ RONK_DEV void radix_network(const F& f, u64 (&x)[16]) {
 // One round: gather the window [wb, wb+4) of the tile index into registers, butterfly, twiddle,
 // scatter back in place.  `lcur` = log2 of the current sub-transform length (only used when NST==4).
 template <int NST, bool INV, class F>
-RONK_DEV void ntt_round(const F& f, u64* smem, const NttTileArgs& A, u32 wb, u32 lcur, u32 t) {
+RONK_DEV void ntt_round(const F& f, u64* smem, const u64* tw, const NttTileArgs& A, u32 wb, u32 lcur, u32 t) {
   const u32 lowmask = (1u << wb) - 1u;
   const u32 e0 = ((t >> wb) << (wb + 4)) | (t & lowmask);
   // The swizzle is XOR-linear and e0 has no bits inside the window, so the 16 addresses are
@@ -126,7 +126,7 @@ RONK_DEV void ntt_round(const F& f, u64* smem, const NttTileArgs& A, u32 wb, u32
       const u32 k1 = ((j & 1) << 3) | ((j & 2) << 1) | ((j & 4) >> 1) | ((j & 8) >> 3);
       u32 idx = (step * k1) & M1;
       if (INV) idx = (0u - idx) & M1;
-      x[j] = f.mul_tw(x[j], ld_tw(A.tw_tile + idx));
+      x[j] = f.mul_tw(x[j], tw[idx]);
     }
   }
   {
@@ -142,6 +142,9 @@ RONK_DEV void ntt_round(const F& f, u64* smem, const NttTileArgs& A, u32 wb, u32
 }
 
 // ---------------- load phase: HBM → shared ----------------
+// Loads are issued LD_BATCH at a time into registers before any is stored, so the HBM latency of a
+// tile is paid once per batch, not once per element.
+constexpr int LD_BATCH = 8;
 template <class F, int MODE>
 RONK_DEV void ntt_load_phase(u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
   const u32 T = 1u << A.tile_log;
@@ -150,22 +153,31 @@ RONK_DEV void ntt_load_phase(u64* smem, const NttTileArgs& A, u32 tile, u32 tid,
     b = tile / A.tiles_per_batch;
     sub = tile - b * A.tiles_per_batch;
   }
-  if (MODE == MODE_SINGLE) {
-    const u64 base = (u64)tile << A.tile_log;
-    for (u32 e = tid; e < T; e += nthr) {
-      const u64 g = base + e;
-      smem[swz(e)] = (g < A.total) ? A.src[g] : 0ULL;
+  u64 base;
+  if (MODE == MODE_SINGLE) base = (u64)tile << A.tile_log;
+  else if (MODE == MODE_PASS1) base = ((u64)b << A.log_n) + ((u64)sub << A.log_c);
+  else base = ((u64)b << A.log_n) + ((u64)sub << A.tile_log);
+  const u32 cmask = (1u << A.log_c) - 1u;
+  for (u32 e0 = tid; e0 < T; e0 += nthr * LD_BATCH) {
+    u64 v[LD_BATCH];
+#pragma unroll
+    for (int i = 0; i < LD_BATCH; i++) {
+      const u32 e = e0 + i * nthr;
+      if (MODE == MODE_SINGLE) {
+        const u64 g = base + e;
+        v[i] = (e < T && g < A.total) ? A.src[g] : 0ULL;
+      } else if (MODE == MODE_PASS1) {
+        const u32 j1 = e >> A.log_c, c = e & cmask;
+        v[i] = (e < T) ? A.src[base + ((u64)j1 << A.log_n2) + c] : 0ULL;
+      } else {
+        v[i] = (e < T) ? A.src[base + e] : 0ULL;
+      }
     }
-  } else if (MODE == MODE_PASS1) {
-    const u64 base = ((u64)b << A.log_n) + ((u64)sub << A.log_c);
-    const u32 cmask = (1u << A.log_c) - 1u;
-    for (u32 e = tid; e < T; e += nthr) {
-      const u32 j1 = e >> A.log_c, c = e & cmask;
-      smem[swz(e)] = A.src[base + ((u64)j1 << A.log_n2) + c];
+#pragma unroll
+    for (int i = 0; i < LD_BATCH; i++) {
+      const u32 e = e0 + i * nthr;
+      if (e < T) smem[swz(e)] = v[i];
     }
-  } else {
-    const u64 base = ((u64)b << A.log_n) + ((u64)sub << A.tile_log);
-    for (u32 e = tid; e < T; e += nthr) smem[swz(e)] = A.src[base + e];
   }
 }
 
@@ -188,12 +200,17 @@ RONK_DEV bool ntt_round_plan(const NttTileArgs& A, u32 r, u32* nst, u32* wb, u32
   return false;
 }
 
+// One round over the whole tile: thread `tid` of `nthr` handles the 16-element groups tid, tid+nthr, …
 template <class F, bool INV>
-RONK_DEV void ntt_round_dispatch(const F& f, u64* smem, const NttTileArgs& A, u32 nst, u32 wb, u32 lcur, u32 tid) {
-  if (nst == 4) ntt_round<4, INV>(f, smem, A, wb, lcur, tid);
-  else if (nst == 3) ntt_round<3, INV>(f, smem, A, wb, 0, tid);
-  else if (nst == 2) ntt_round<2, INV>(f, smem, A, wb, 0, tid);
-  else ntt_round<1, INV>(f, smem, A, wb, 0, tid);
+RONK_DEV void ntt_round_dispatch(const F& f, u64* smem, const u64* tw, const NttTileArgs& A, u32 nst, u32 wb, u32 lcur,
+                                 u32 tid, u32 nthr) {
+  const u32 groups = (1u << A.tile_log) >> 4;
+  for (u32 t = tid; t < groups; t += nthr) {
+    if (nst == 4) ntt_round<4, INV>(f, smem, tw, A, wb, lcur, t);
+    else if (nst == 3) ntt_round<3, INV>(f, smem, tw, A, wb, 0, t);
+    else if (nst == 2) ntt_round<2, INV>(f, smem, tw, A, wb, 0, t);
+    else ntt_round<1, INV>(f, smem, tw, A, wb, 0, t);
+  }
 }
 
 // ---------------- store phase: shared → HBM (un-bit-reverse on the fly) ----------------
@@ -257,7 +274,7 @@ struct NttShape {
 };
 inline NttShape ntt_shape(u32 log_n) {
   NttShape s;
-  s.two_pass = log_n > 14;
+  s.two_pass = log_n > 13;  // tile (128 KiB) + twiddle table must fit in 227 KiB of shared memory
   s.log_n1 = s.two_pass ? (log_n + 1) / 2 : log_n;
   s.log_n2 = s.two_pass ? log_n / 2 : 0;
   return s;
@@ -334,18 +351,57 @@ inline NttTileArgs ntt_args_pass2(const u64* ws, u64* data, const u64* mul, cons
 }
 
 #if defined(__CUDACC__)
-template <class F, int MODE, bool INV>
-__global__ void __launch_bounds__(1024, 1) ntt_tile_kernel(const F f, const NttTileArgs A) {
-  extern __shared__ __align__(16) u64 smem[];
-  const u32 nthr = blockDim.x, tid = threadIdx.x, tile = blockIdx.x;
-  ntt_load_phase<F, MODE>(smem, A, tile, tid, nthr);
+// --- TMA (bulk async copy) staging of the twiddle table into shared memory ---------------------
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"((u32)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u32 bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (u32)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((u32)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+// Shared memory: [ tile: T·8 B | twiddles: M·8 B | mbarrier: 8 B ]
+template <class F, int MODE, bool INV, int NTHR>
+__global__ void __launch_bounds__(NTHR, 1) ntt_tile_kernel(const F f, const NttTileArgs A) {
+  extern __shared__ __align__(128) u64 smem[];
+  const u32 tid = threadIdx.x, tile = blockIdx.x;
+  const u32 T = 1u << A.tile_log, M = 1u << A.log_m;
+  u64* tw = smem + T;
+  u64* bar = tw + M;
+  const bool use_tw = A.log_m > 4;  // a single radix-16 round has no general twiddles
+  if (use_tw && tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar, M * 8u);
+    tma_bulk_g2s(tw, A.tw_tile, M * 8u, bar);  // lands while the tile itself is being loaded
+  }
+  ntt_load_phase<F, MODE>(smem, A, tile, tid, NTHR);
   __syncthreads();
+  if (use_tw) mbar_wait(bar, 0);
   u32 nst, wb, lcur;
   for (u32 r = 0; ntt_round_plan(A, r, &nst, &wb, &lcur); r++) {
-    ntt_round_dispatch<F, INV>(f, smem, A, nst, wb, lcur, tid);
+    ntt_round_dispatch<F, INV>(f, smem, tw, A, nst, wb, lcur, tid, NTHR);
     __syncthreads();
   }
-  ntt_store_phase<F, MODE, INV>(f, smem, A, tile, tid, nthr);
+  ntt_store_phase<F, MODE, INV>(f, smem, A, tile, tid, NTHR);
 }
 
 // tab[i] = to_tw(w^i · s) for i < count  (plan building; w, s plain residues)

@@ -165,7 +165,7 @@ static int poly_mul_with_field(ronk_ctx* ctx, const F& f, u64 p, u64 g, const u6
   const size_t L = da + db - 1;
   u32 log_n = 0;
   while (((size_t)1 << log_n) < L) log_n++;
-  const bool ntt_ok = g != 0 && log_n >= 1 && log_n <= 28 && (p - 1) % ((u64)1 << log_n) == 0;
+  const bool ntt_ok = g != 0 && log_n >= 1 && log_n <= 26 && (p - 1) % ((u64)1 << log_n) == 0;
   // NTT cost ~ 3·n·log n / 2 multiplies vs da·db for schoolbook
   const double school = (double)da * (double)db;
   const double viantt = 1.5 * (double)((size_t)1 << log_n) * (double)log_n + 4096.0;

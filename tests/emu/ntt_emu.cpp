@@ -48,13 +48,13 @@ std::vector<u64> table(const F& f, u64 w, u64 s, u64 count) {  // pow_table_kern
 
 template <class F, int MODE, bool INV>
 void run_tiles(const F& f, const NttTileArgs& A, u64 tiles) {
-  const u32 T = 1u << A.tile_log, nthr = T / 16;
+  const u32 T = 1u << A.tile_log, nthr = (T / 16 >= 512) ? 512 : T / 16;
   std::vector<u64> smem(T);
   for (u64 tile = 0; tile < tiles; tile++) {
     for (u32 t = 0; t < nthr; t++) ntt_load_phase<F, MODE>(smem.data(), A, (u32)tile, t, nthr);
     u32 nst, wb, lcur;
     for (u32 r = 0; ntt_round_plan(A, r, &nst, &wb, &lcur); r++)
-      for (u32 t = 0; t < nthr; t++) ntt_round_dispatch<F, INV>(f, smem.data(), A, nst, wb, lcur, t);
+      for (u32 t = 0; t < nthr; t++) ntt_round_dispatch<F, INV>(f, smem.data(), A.tw_tile, A, nst, wb, lcur, t, nthr);
     for (u32 t = 0; t < nthr; t++) ntt_store_phase<F, MODE, INV>(f, smem.data(), A, (u32)tile, t, nthr);
   }
 }
@@ -94,7 +94,7 @@ extern "C" {
 // Same contract as ronk_ntt_u64 / ronk_ntt_mul_u64, on host memory.
 int emu_ntt(uint64_t p, uint64_t g, uint64_t* data, const uint64_t* mul, uint32_t log_n, uint32_t batch, int inverse,
             uint32_t tile_cap) {
-  if (log_n == 0 || log_n > 28 || (p - 1) % ((u64)1 << log_n) != 0) return 1;
+  if (log_n == 0 || log_n > 26 || (p - 1) % ((u64)1 << log_n) != 0) return 1;
   if (p == GL_P && g == 7) {
     GoldilocksField f;
     return inverse ? run<GoldilocksField, true>(f, p, g, true, data, mul, log_n, batch, tile_cap)

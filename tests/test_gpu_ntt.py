@@ -167,7 +167,7 @@ def test_host_pointer_variant_and_errors():
     with pytest.raises(RonkPanic):   # 2^33 ∤ p-1
         c.call("ronk_ntt_u64", GL, 7, dev(a).data_ptr(), 33, 1, 0)
     with pytest.raises(RonkError) as ei:
-        c.call("ronk_ntt_u64", GL, 7, dev(a).data_ptr(), 29, 1, 0)
+        c.call("ronk_ntt_u64", GL, 7, dev(a).data_ptr(), 27, 1, 0)
     assert ei.value.code == 5
     with pytest.raises(RonkPanic):   # composite modulus
         c.call("ronk_ntt_u64", 100, 7, dev(a).data_ptr(), 2, 1, 0)
