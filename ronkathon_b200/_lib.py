@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libronk_b200.so")
+LIB_PATH = os.environ.get("RONK_LIB_PATH") or os.path.join(_HERE, "libronk_b200.so")  # override: experiments only
 
 OK, EINVAL, ECUDA, ENOMEM, ENCCL, EUNSUPPORTED = 0, 1, 2, 3, 4, 5
 GOLDILOCKS = 0xFFFFFFFF00000001

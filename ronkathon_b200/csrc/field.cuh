@@ -132,10 +132,16 @@ struct GoldilocksField {
     } else {
       const u32 a0 = (u32)a, a1 = (u32)(a >> 32);
       constexpr int s = S % 32;
-      // (y2:y1:y0) = a << s  (96 bits)
-      const u32 y0 = a0 << s;
-      const u32 y1 = s ? __funnelshift_l(a0, a1, s) : a1;
-      const u32 y2 = s ? (a1 >> (32 - s)) : 0u;
+      // (y2:y1:y0) = a << s (96 bits), as a·2^s on the FMA pipe (two IMAD.WIDE) — the ALU pipe is
+      // the bottleneck of the butterfly network, the multiplier is not.
+      u32 y0, y1, y2;
+      if constexpr (s == 0) {
+        y0 = a0; y1 = a1; y2 = 0u;
+      } else {
+        const u64 lo = (u64)a0 * (u64)(1u << s);
+        const u64 hi = (u64)a1 * (u64)(1u << s) + (lo >> 32);   // no overflow: < 2^(32+s)
+        y0 = (u32)lo; y1 = (u32)hi; y2 = (u32)(hi >> 32);
+      }
       if constexpr (S < 32) return reduce_words(y0, y1, y2, 0u);
       else if constexpr (S < 64) return reduce_words(0u, y0, y1, y2);
       else {

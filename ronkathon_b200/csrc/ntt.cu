@@ -69,36 +69,32 @@ static int build_plan(ronk_ctx* ctx, const F& f, u64 p, u64 g, u32 log_n, NttPla
   return RONK_OK;
 }
 
-template <class F, int MODE, bool INV, int NTHR>
+template <class F, int MODE, bool INV, int NTHR, int MINB>
 static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
   const size_t smem = ((size_t)1 << A.tile_log) * sizeof(u64) + ((size_t)1 << A.log_m) * sizeof(u64) + 16;
   static bool attr_done = false;  // one device per process in practice; re-set is harmless
   if (!attr_done) {
-    RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_tile_kernel<F, MODE, INV, NTHR>,
+    RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_tile_kernel<F, MODE, INV, NTHR, MINB>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_done = true;
   }
   {
     LaunchScope ls(ctx, name);
-    ntt_tile_kernel<F, MODE, INV, NTHR><<<tiles, NTHR, smem, ctx->stream>>>(f, A);
+    ntt_tile_kernel<F, MODE, INV, NTHR, MINB><<<tiles, NTHR, smem, ctx->stream>>>(f, A);
   }
   return check_launch(ctx, name);
 }
 
-// CTA size: one thread per 16 tile elements up to 512 threads (128 registers each, no spills);
-// RONK_NTT_THREADS=1024 selects the 64-register variant for experiments.
+// CTA shape: every thread owns 32 tile elements per round (two radix-16 groups, ≤128 registers, no
+// spills).  A 2^14 tile is one 512-thread CTA per SM; a 2^13 tile is a 256-thread CTA and two of
+// them share an SM, so one CTA's load/store phases overlap the other's butterflies.
 template <class F, int MODE, bool INV>
 static int launch_tile(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
   const u32 groups = (1u << A.tile_log) / 16;
-  static int pref = 0;
-  if (!pref) {
-    const char* s = getenv("RONK_NTT_THREADS");
-    pref = s ? atoi(s) : 512;
-  }
-  if (groups >= 1024 && pref >= 1024) return launch_tile_n<F, MODE, INV, 1024>(ctx, f, A, tiles, name);
-  if (groups >= 512) return launch_tile_n<F, MODE, INV, 512>(ctx, f, A, tiles, name);
-  if (groups >= 128) return launch_tile_n<F, MODE, INV, 128>(ctx, f, A, tiles, name);
-  return launch_tile_n<F, MODE, INV, 32>(ctx, f, A, tiles, name);
+  if (groups >= 1024) return launch_tile_n<F, MODE, INV, 512, 1>(ctx, f, A, tiles, name);
+  if (groups >= 512) return launch_tile_n<F, MODE, INV, 256, 2>(ctx, f, A, tiles, name);
+  if (groups >= 128) return launch_tile_n<F, MODE, INV, 128, 2>(ctx, f, A, tiles, name);
+  return launch_tile_n<F, MODE, INV, 32, 2>(ctx, f, A, tiles, name);
 }
 
 template <class F, bool INV>
@@ -115,13 +111,22 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
   }
   const size_t bytes = ((size_t)batch << log_n) * sizeof(u64);
   RONK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, bytes));
+  static int pref1 = 0, pref2 = 0;  // preferred tile sizes (log2); RONK_TILE1 / RONK_TILE2 for experiments
+  if (!pref1) {
+    const char* s1 = getenv("RONK_TILE1");
+    const char* s2 = getenv("RONK_TILE2");
+    pref1 = s1 ? atoi(s1) : 14;  // measured best on B200: strided pass-1 reads want 32-byte segments
+    pref2 = s2 ? atoi(s2) : 13;
+  }
+  u32 tile1, tile2;
+  ntt_pass_tiles(log_n, (u32)pref1, (u32)pref2, &tile1, &tile2);
   // pass 1: N1-point transforms down the columns, inter-pass twiddle, blocked write to the workspace
-  const NttTileArgs A1 =
-      ntt_args_pass1(data, (u64*)ctx->ws, pl.tw1, pl.tw_lo, INV ? pl.tw_hi_inv : pl.tw2, log_n, batch, &tiles);
+  const NttTileArgs A1 = ntt_args_pass1(data, (u64*)ctx->ws, pl.tw1, pl.tw_lo, INV ? pl.tw_hi_inv : pl.tw2, log_n,
+                                        batch, tile1, tile2, &tiles);
   if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
   RONK_TRY((launch_tile<F, MODE_PASS1, INV>(ctx, f, A1, (u32)tiles, INV ? "intt_pass1" : "ntt_pass1")));
   // pass 2: N2-point transforms along the contiguous workspace tiles, natural-order output
-  const NttTileArgs A2 = ntt_args_pass2((const u64*)ctx->ws, data, mul, pl.tw2, log_n, batch, &tiles);
+  const NttTileArgs A2 = ntt_args_pass2((const u64*)ctx->ws, data, mul, pl.tw2, log_n, batch, tile2, &tiles);
   if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
   return launch_tile<F, MODE_PASS2, INV>(ctx, f, A2, (u32)tiles, INV ? "intt_pass2" : "ntt_pass2");
 }

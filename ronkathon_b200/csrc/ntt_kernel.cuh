@@ -144,7 +144,10 @@ RONK_DEV void ntt_round(const F& f, u64* smem, const u64* tw, const NttTileArgs&
 // ---------------- load phase: HBM → shared ----------------
 // Loads are issued LD_BATCH at a time into registers before any is stored, so the HBM latency of a
 // tile is paid once per batch, not once per element.
-constexpr int LD_BATCH = 8;
+#ifndef RONK_LD_BATCH
+#define RONK_LD_BATCH 8
+#endif
+constexpr int LD_BATCH = RONK_LD_BATCH;
 template <class F, int MODE>
 RONK_DEV void ntt_load_phase(u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
   const u32 T = 1u << A.tile_log;
@@ -307,8 +310,15 @@ inline NttTileArgs ntt_args_single(u64* data, const u64* mul, const u64* tw, u64
   *tiles = (total + ((u64)1 << tile_log) - 1) >> tile_log;
   return A;
 }
+// Tile sizes of the two passes (log2 elements).  `pref` = preferred size (13 → two CTAs per SM);
+// a tile can never be smaller than one transform of that pass.
+inline void ntt_pass_tiles(u32 log_n, u32 pref1, u32 pref2, u32* t1, u32* t2) {
+  const NttShape sh = ntt_shape(log_n);
+  *t1 = pref1 < sh.log_n1 ? sh.log_n1 : (pref1 > NTT_TILE_LOG_MAX ? NTT_TILE_LOG_MAX : pref1);
+  *t2 = pref2 < sh.log_n2 ? sh.log_n2 : (pref2 > NTT_TILE_LOG_MAX ? NTT_TILE_LOG_MAX : pref2);
+}
 inline NttTileArgs ntt_args_pass1(const u64* data, u64* ws, const u64* tw1, const u64* tw_lo, const u64* tw_hi,
-                                  u32 log_n, u32 batch, u64* tiles) {
+                                  u32 log_n, u32 batch, u32 tile1, u32 tile2, u64* tiles) {
   const NttShape sh = ntt_shape(log_n);
   NttTileArgs A = {};
   A.src = data;
@@ -316,29 +326,29 @@ inline NttTileArgs ntt_args_pass1(const u64* data, u64* ws, const u64* tw1, cons
   A.tw_tile = tw1;
   A.tw_lo = tw_lo;
   A.tw_hi = tw_hi;
-  A.tile_log = NTT_TILE_LOG_MAX;
+  A.tile_log = tile1;
   A.log_m = sh.log_n1;
-  A.log_c = NTT_TILE_LOG_MAX - sh.log_n1;
+  A.log_c = tile1 - sh.log_n1;
   A.log_n = log_n;
   A.log_n1 = sh.log_n1;
   A.log_n2 = sh.log_n2;
-  A.log_c2 = NTT_TILE_LOG_MAX - sh.log_n2;
+  A.log_c2 = tile2 - sh.log_n2;
   A.log_lo = sh.log_n1;
   A.tiles_per_batch = 1u << (sh.log_n2 - A.log_c);
   *tiles = (u64)batch * A.tiles_per_batch;
   return A;
 }
 inline NttTileArgs ntt_args_pass2(const u64* ws, u64* data, const u64* mul, const u64* tw2, u32 log_n, u32 batch,
-                                  u64* tiles) {
+                                  u32 tile2, u64* tiles) {
   const NttShape sh = ntt_shape(log_n);
   NttTileArgs A = {};
   A.src = ws;
   A.dst = data;
   A.tw_tile = tw2;
   A.mul_src = mul;
-  A.tile_log = NTT_TILE_LOG_MAX;
+  A.tile_log = tile2;
   A.log_m = sh.log_n2;
-  A.log_c = NTT_TILE_LOG_MAX - sh.log_n2;
+  A.log_c = tile2 - sh.log_n2;
   A.log_n = log_n;
   A.log_n1 = sh.log_n1;
   A.log_n2 = sh.log_n2;
@@ -379,8 +389,8 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
 }
 
 // Shared memory: [ tile: T·8 B | twiddles: M·8 B | mbarrier: 8 B ]
-template <class F, int MODE, bool INV, int NTHR>
-__global__ void __launch_bounds__(NTHR, 1) ntt_tile_kernel(const F f, const NttTileArgs A) {
+template <class F, int MODE, bool INV, int NTHR, int MINB>
+__global__ void __launch_bounds__(NTHR, MINB) ntt_tile_kernel(const F f, const NttTileArgs A) {
   extern __shared__ __align__(128) u64 smem[];
   const u32 tid = threadIdx.x, tile = blockIdx.x;
   const u32 T = 1u << A.tile_log, M = 1u << A.log_m;

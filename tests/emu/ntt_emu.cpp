@@ -48,7 +48,7 @@ std::vector<u64> table(const F& f, u64 w, u64 s, u64 count) {  // pow_table_kern
 
 template <class F, int MODE, bool INV>
 void run_tiles(const F& f, const NttTileArgs& A, u64 tiles) {
-  const u32 T = 1u << A.tile_log, nthr = (T / 16 >= 512) ? 512 : T / 16;
+  const u32 T = 1u << A.tile_log, nthr = (T / 32 >= 32) ? T / 32 : 32;
   std::vector<u64> smem(T);
   for (u64 tile = 0; tile < tiles; tile++) {
     for (u32 t = 0; t < nthr; t++) ntt_load_phase<F, MODE>(smem.data(), A, (u32)tile, t, nthr);
@@ -60,7 +60,8 @@ void run_tiles(const F& f, const NttTileArgs& A, u64 tiles) {
 }
 
 template <class F, bool INV>
-int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 log_n, u32 batch, u32 tile_cap) {
+int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 log_n, u32 batch, u32 tile_cap,
+        u32 pref1, u32 pref2) {
   const u64 n = (u64)1 << log_n;
   const u64 w = h_powmod(g, (p - 1) / n, p);
   const u64 ninv = h_powmod(n % p, p - 2, p);
@@ -79,10 +80,12 @@ int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 l
   auto tw_lo = table(f, w, 1, n1);
   auto tw_hi_inv = table(f, h_powmod(w, n1, p), ninv, n2);
   std::vector<u64> ws((size_t)batch << log_n);
-  NttTileArgs A1 =
-      ntt_args_pass1(data, ws.data(), tw1.data(), tw_lo.data(), INV ? tw_hi_inv.data() : tw2.data(), log_n, batch, &tiles);
+  u32 tile1, tile2;
+  ntt_pass_tiles(log_n, pref1, pref2, &tile1, &tile2);
+  NttTileArgs A1 = ntt_args_pass1(data, ws.data(), tw1.data(), tw_lo.data(), INV ? tw_hi_inv.data() : tw2.data(), log_n,
+                                  batch, tile1, tile2, &tiles);
   run_tiles<F, MODE_PASS1, INV>(f, A1, tiles);
-  NttTileArgs A2 = ntt_args_pass2(ws.data(), data, mul, tw2.data(), log_n, batch, &tiles);
+  NttTileArgs A2 = ntt_args_pass2(ws.data(), data, mul, tw2.data(), log_n, batch, tile2, &tiles);
   run_tiles<F, MODE_PASS2, INV>(f, A2, tiles);
   return 0;
 }
@@ -93,16 +96,16 @@ extern "C" {
 
 // Same contract as ronk_ntt_u64 / ronk_ntt_mul_u64, on host memory.
 int emu_ntt(uint64_t p, uint64_t g, uint64_t* data, const uint64_t* mul, uint32_t log_n, uint32_t batch, int inverse,
-            uint32_t tile_cap) {
+            uint32_t tile_cap, uint32_t pref1, uint32_t pref2) {
   if (log_n == 0 || log_n > 26 || (p - 1) % ((u64)1 << log_n) != 0) return 1;
   if (p == GL_P && g == 7) {
     GoldilocksField f;
-    return inverse ? run<GoldilocksField, true>(f, p, g, true, data, mul, log_n, batch, tile_cap)
-                   : run<GoldilocksField, false>(f, p, g, true, data, mul, log_n, batch, tile_cap);
+    return inverse ? run<GoldilocksField, true>(f, p, g, true, data, mul, log_n, batch, tile_cap, pref1, pref2)
+                   : run<GoldilocksField, false>(f, p, g, true, data, mul, log_n, batch, tile_cap, pref1, pref2);
   }
   MontField f = make_mont(p, g, inverse != 0);
-  return inverse ? run<MontField, true>(f, p, g, false, data, mul, log_n, batch, tile_cap)
-                 : run<MontField, false>(f, p, g, false, data, mul, log_n, batch, tile_cap);
+  return inverse ? run<MontField, true>(f, p, g, false, data, mul, log_n, batch, tile_cap, pref1, pref2)
+                 : run<MontField, false>(f, p, g, false, data, mul, log_n, batch, tile_cap, pref1, pref2);
 }
 
 // Field-policy arithmetic, element-wise, for cross-checks against the oracle.

@@ -26,7 +26,7 @@ def emu():
     if not os.path.exists(so) or os.path.getmtime(so) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src])
     lib = C.CDLL(so)
-    lib.emu_ntt.argtypes = [C.c_uint64, C.c_uint64, P64, P64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32]
+    lib.emu_ntt.argtypes = [C.c_uint64, C.c_uint64, P64, P64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
     lib.emu_field_op.argtypes = [C.c_uint64, C.c_int, P64, P64, P64, C.c_uint64, C.c_int]
     lib.emu_gl_w16.argtypes = [C.c_uint64, P64]
     lib.emu_swizzle_worst_conflict.argtypes = [C.c_uint32, C.c_uint32]
@@ -37,10 +37,10 @@ def _ptr(a):
     return a.ctypes.data_as(P64) if a is not None else None
 
 
-def emu_ntt(emu, p, g, data, log_n, batch=1, inverse=False, mul=None, tile_cap=12):
+def emu_ntt(emu, p, g, data, log_n, batch=1, inverse=False, mul=None, tile_cap=12, tiles=(13, 13)):
     d = np.ascontiguousarray(data, dtype=np.uint64).copy()
     m = None if mul is None else np.ascontiguousarray(mul, dtype=np.uint64)
-    rc = emu.emu_ntt(p, g, _ptr(d), _ptr(m), log_n, batch, int(inverse), tile_cap)
+    rc = emu.emu_ntt(p, g, _ptr(d), _ptr(m), log_n, batch, int(inverse), tile_cap, tiles[0], tiles[1])
     assert rc == 0
     return d
 
@@ -132,14 +132,15 @@ def test_emulated_golden_vectors(emu, gold64):
     assert list(emu_ntt(emu, GL, 7, a, 10)) == gold64["ntt_2_10_full"]
 
 
-@pytest.mark.parametrize("log_n,batch", [(15, 1), (16, 2), (17, 1), (18, 1)])
-def test_emulated_goldilocks_two_pass(emu, log_n, batch):
+@pytest.mark.parametrize("tiles", [(13, 13), (14, 14), (13, 14), (14, 13), (12, 12)])
+@pytest.mark.parametrize("log_n,batch", [(14, 2), (15, 1), (16, 2), (17, 1), (18, 1)])
+def test_emulated_goldilocks_two_pass(emu, log_n, batch, tiles):
     n = 1 << log_n
     a = oracle.splitmix(GL, 42, n * batch)
-    X = emu_ntt(emu, GL, 7, a, log_n, batch)
+    X = emu_ntt(emu, GL, 7, a, log_n, batch, tiles=tiles)
     for b in range(batch):
         assert np.array_equal(X[b * n:(b + 1) * n], oracle.ntt_fast(GL, a[b * n:(b + 1) * n]))
-    assert np.array_equal(emu_ntt(emu, GL, 7, X, log_n, batch, inverse=True), a)
+    assert np.array_equal(emu_ntt(emu, GL, 7, X, log_n, batch, inverse=True, tiles=tiles), a)
 
 
 def test_emulated_two_pass_generic_and_fused_mul(emu, gold64):
