@@ -106,6 +106,15 @@ int ronk_ntt_mul_u64(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *data, cons
 int ronk_dft_u64(ronk_ctx *ctx, uint64_t p, uint64_t g, const uint64_t *in, uint64_t n, uint64_t *out);
 int ronk_dft_u64_host(ronk_ctx *ctx, uint64_t p, uint64_t g, const uint64_t *in, uint64_t n, uint64_t *out);
 
+/* Distributed-transform building blocks (the top log2(G) stages of one large NTT across
+ * G GPUs).  out[i] = scale * base^i — the twiddle column ω_n^(r·k') a rank multiplies into its
+ * local transform before the exchange. */
+int ronk_field_powers_u64(ronk_ctx *ctx, uint64_t p, uint64_t base, uint64_t scale, uint64_t *out, size_t n);
+/* In-place 2^log_g-point transforms (log_g ≤ 4) over the strided sets {data[k + j*stride]}, j < 2^log_g,
+ * for k < count: the cross-rank radix-G butterflies after the all-to-all.  Same ω convention as
+ * ronk_ntt_u64 (ω_G = g^((p-1)/G)); inverse applies G^-1. */
+int ronk_ntt_strided_small_u64(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *data, uint32_t log_g, size_t stride, size_t count, int inverse);
+
 /* ---- Polynomial<Monomial, F, D> ----------------------------------------------------------- */
 /* Mul — src/polynomial/arithmetic.rs:97-119.  c has da+db-1 coefficients (no trimming).
  * NTT path (pad → NTT, NTT∘pointwise → iNTT) when a power of two ≥ da+db-1 divides p-1 and

@@ -40,6 +40,37 @@ __global__ void unop_kernel(const F f, const u64* a, u64* out, size_t n, u64 e, 
   }
 }
 
+// out[i] = scale·base^i
+template <class F>
+__global__ void powers_kernel(const F f, u64 base, u64 scale, u64* out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= n) return;
+  u64 cur = f.mul(scale, field_pow(f, base, (u64)i0));
+  const u64 step = field_pow(f, base, (u64)stride);
+  for (size_t i = i0; i < n; i += stride) {
+    out[i] = cur;
+    cur = f.mul(cur, step);
+  }
+}
+
+// In-place G-point DFT (G = 2^log_g ≤ 16) over data[k + j·stride]; wt[j] = ω_G^(±j) plain residues,
+// sc = 1 or G^-1.  O(G²) per k — the cross-rank stage is a sliver of the whole transform.
+template <class F>
+__global__ void strided_dft_kernel(const F f, u64* data, u32 G, size_t stride, size_t count, const u64* wt, u64 sc) {
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += step) {
+    u64 x[16], y[16];
+    for (u32 j = 0; j < G; j++) x[j] = data[k + (size_t)j * stride];
+    for (u32 q = 0; q < G; q++) {
+      u64 acc = 0;
+      for (u32 j = 0; j < G; j++) acc = f.add(acc, f.mul(x[j], wt[(j * q) & (G - 1)]));
+      y[q] = f.mul(acc, sc);
+    }
+    for (u32 q = 0; q < G; q++) data[k + (size_t)q * stride] = y[q];
+  }
+}
+
 __global__ void splitmix_kernel(u64 p, u64 seed, u64* out, size_t n) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -206,6 +237,58 @@ int ronk_field_inv_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, uint64_t* o
 }
 int ronk_field_pow_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, uint64_t e, uint64_t* out, size_t n) {
   return unop<2>(ctx, p, (const u64*)a, (u64*)out, n, e, "field_pow");
+}
+
+int ronk_field_powers_u64(ronk_ctx* ctx, uint64_t p, uint64_t base, uint64_t scale, uint64_t* out, size_t n) {
+  if (!ctx || (n && !out)) return set_err(ctx, RONK_EINVAL, "null argument");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (base >= p || scale >= p) return set_err(ctx, RONK_EINVAL, "non-canonical argument");
+  if (n == 0) return RONK_OK;
+  const int threads = 256, blocks = grid_for(ctx, (n + 7) / 8, threads);
+  if (p == GL_P) {
+    GoldilocksField f;
+    LaunchScope ls(ctx, "field_powers");
+    powers_kernel<GoldilocksField><<<blocks, threads, 0, ctx->stream>>>(f, base, scale, (u64*)out, n);
+  } else {
+    MontField f;
+    RONK_TRY(make_mont_field(ctx, p, 0, false, &f));
+    LaunchScope ls(ctx, "field_powers");
+    powers_kernel<MontField><<<blocks, threads, 0, ctx->stream>>>(f, base, scale, (u64*)out, n);
+  }
+  return check_launch(ctx, "powers_kernel");
+}
+
+int ronk_ntt_strided_small_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* data, uint32_t log_g, size_t stride,
+                               size_t count, int inverse) {
+  if (!ctx || (count && !data)) return set_err(ctx, RONK_EINVAL, "null argument");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (g == 0 || g >= p) return set_err(ctx, RONK_EINVAL, "generator out of range");
+  if (log_g > 4) return set_err(ctx, RONK_EUNSUPPORTED, "log_g > 4 not supported");
+  const u64 G = (u64)1 << log_g;
+  if ((p - 1) % G != 0) return set_err(ctx, RONK_EINVAL, "n must divide p - 1 (no primitive n-th root of unity)");
+  if (count == 0 || log_g == 0) return RONK_OK;
+  u64 w = h_powmod(g, (p - 1) / G, p);
+  if (inverse) w = h_powmod(w, p - 2, p);
+  u64 h_wt[16];
+  for (u64 j = 0; j < G; j++) h_wt[j] = h_powmod(w, j, p);
+  const u64 sc = inverse ? h_powmod(G % p, p - 2, p) : 1 % p;
+  RONK_TRY(ensure_ws(ctx, &ctx->ws2, &ctx->ws2_bytes, 16 * sizeof(u64)));
+  RONK_CUDA(ctx, cudaMemcpyAsync(ctx->ws2, h_wt, G * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // h_wt is a stack buffer
+  const int threads = 128, blocks = grid_for(ctx, count, threads);
+  if (p == GL_P) {
+    GoldilocksField f;
+    LaunchScope ls(ctx, "ntt_cross_rank");
+    strided_dft_kernel<GoldilocksField><<<blocks, threads, 0, ctx->stream>>>(f, (u64*)data, (u32)G, stride, count,
+                                                                             (const u64*)ctx->ws2, sc);
+  } else {
+    MontField f;
+    RONK_TRY(make_mont_field(ctx, p, 0, false, &f));
+    LaunchScope ls(ctx, "ntt_cross_rank");
+    strided_dft_kernel<MontField><<<blocks, threads, 0, ctx->stream>>>(f, (u64*)data, (u32)G, stride, count,
+                                                                       (const u64*)ctx->ws2, sc);
+  }
+  return check_launch(ctx, "strided_dft_kernel");
 }
 
 int ronk_splitmix_fill_u64(ronk_ctx* ctx, uint64_t p, uint64_t seed, uint64_t* out, size_t n) {

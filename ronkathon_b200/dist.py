@@ -1,0 +1,130 @@
+"""Multi-GPU layer: one process per GPU, `torch.distributed` for the plumbing.
+
+Three shardings of the hot path:
+
+* batched transforms (BASELINE config 5): independent units, contiguous batch ranges per rank,
+  NO collective on the data path (`shard_range`, `ntt_batch_sharded`);
+* one large transform across G = world_size GPUs: rank r owns the decimated slice a[r::G]; a local
+  n/G-point NTT, the twiddle column ω_n^(r·k'), ONE all-to-all, then G-point butterflies across the
+  received blocks (`ntt_distributed`).  Output is block-cyclic: rank s ends with
+  X[s·m/G + k'' + m·q] at position q·(m/G) + k'' (m = n/G);
+* kzg::commit: index-range shards → 17 bucket sums per rank → one all-gather of 68 bytes → local
+  combine (`msm_distributed`).
+
+The per-rank compute goes through `LocalOps`; the default implementation calls the CUDA kernels in
+libronk_b200.so.  Tests substitute a CPU stand-in so the sharding / exchange logic runs under the
+`gloo` backend without a GPU (the stand-in lives in tests/, not here: no CPU path in the product).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import GOLDILOCKS
+
+
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous [lo, hi) range of `total` units owned by `rank` (remainder spread over the first ranks)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class LocalOps:
+    """Per-rank compute used by the distributed algorithms, on libronk_b200.so."""
+
+    def __init__(self, ctx, p: int = GOLDILOCKS, g: int = 7):
+        self.ctx, self.p, self.g = ctx, p, g
+
+    def root_of_unity(self, n: int) -> int:
+        import ctypes as C
+        out = C.c_uint64()
+        if _lib.lib().ronk_root_of_unity(self.p, self.g, n, C.byref(out)) != 0:
+            raise _lib.RonkPanic(1, "n must divide p - 1")
+        return out.value
+
+    def ntt(self, x, log_n: int, batch: int = 1, inverse: bool = False):
+        self.ctx.call("ronk_ntt_u64", self.p, self.g, _lib._ptr(x), log_n, batch, int(inverse))
+        return x
+
+    def mul_powers(self, x, base: int, scale: int = 1):
+        """x[i] *= scale·base^i"""
+        tab = torch.empty_like(x)
+        self.ctx.call("ronk_field_powers_u64", self.p, base, scale, _lib._ptr(tab), x.numel())
+        self.ctx.call("ronk_field_mul_u64", self.p, _lib._ptr(x), _lib._ptr(tab), _lib._ptr(x), x.numel())
+        return x
+
+    def cross_dft(self, x, log_g: int, stride: int, count: int, inverse: bool = False):
+        self.ctx.call("ronk_ntt_strided_small_u64", self.p, self.g, _lib._ptr(x), log_g, stride, count, int(inverse))
+        return x
+
+    def msm_buckets(self, points, scalars) -> bytes:
+        from . import ops
+        return ops.msm_buckets(self.ctx, points, scalars)
+
+    def msm_combine(self, sets: bytes) -> bytes:
+        from . import ops
+        return ops.msm_combine(self.ctx, sets)
+
+    def sync(self):
+        self.ctx.sync()
+
+
+def ntt_batch_sharded(ops: LocalOps, shard, log_n: int, inverse: bool = False):
+    """Config-5 path: this rank's contiguous slice of the batch, transformed in place. No collective."""
+    n = 1 << log_n
+    assert shard.numel() % n == 0
+    return ops.ntt(shard, log_n, shard.numel() // n, inverse)
+
+
+def ntt_distributed(ops: LocalOps, local, log_n: int, group=None):
+    """Forward transform of ONE 2^log_n-point polynomial spread cyclically over the group.
+
+    `local` holds a[rank::G] (length m = n/G, int64 view of uint64 residues).  Returns a tensor of
+    length m laid out [q][k''] with value X[(rank·m/G + k'') + m·q]."""
+    G = dist.get_world_size(group)
+    r = dist.get_rank(group)
+    log_g = G.bit_length() - 1
+    assert 1 << log_g == G, "world size must be a power of two"
+    n = 1 << log_n
+    m = n // G
+    assert local.numel() == m and m % G == 0
+    ops.ntt(local, log_n - log_g)                       # Y_r[k'] = Σ_j a[r + Gj] ω_m^(jk')
+    if r:
+        ops.mul_powers(local, pow(ops.root_of_unity(n), r, ops.p))  # Z_r[k'] = ω_n^(r k') Y_r[k']
+    ops.sync()
+    recv = torch.empty_like(local)
+    dist.all_to_all_single(recv, local, group=group)    # recv[r'][k''] = Z_r'[rank·m/G + k'']
+    ops.cross_dft(recv, log_g, m // G, m // G)          # X[k' + m q] = Σ_r' ω_G^(r' q) Z_r'[k']
+    ops.sync()
+    return recv
+
+
+def gather_distributed_output(out, log_n: int, group=None):
+    """Collect ntt_distributed's block-cyclic outputs into natural order on every rank (tests / small n)."""
+    G = dist.get_world_size(group)
+    n = 1 << log_n
+    m = n // G
+    parts = [torch.empty_like(out) for _ in range(G)]
+    dist.all_gather(parts, out, group=group)
+    full = torch.empty(n, dtype=out.dtype, device=out.device)
+    for s, part in enumerate(parts):
+        blk = part.view(G, m // G)
+        for q in range(G):
+            lo = s * (m // G) + m * q
+            full[lo:lo + m // G] = blk[q]
+    return full
+
+
+def msm_distributed(ops: LocalOps, points_shard, scalars_shard, group=None) -> bytes:
+    """kzg::commit over index-range shards: all-gather of the 17 bucket sums, local combine."""
+    mine = ops.msm_buckets(points_shard, scalars_shard)
+    G = dist.get_world_size(group)
+    send = torch.tensor(list(mine), dtype=torch.uint8)
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        send = send.cuda()
+    parts = [torch.empty_like(send) for _ in range(G)]
+    dist.all_gather(parts, send, group=group)
+    return ops.msm_combine(b"".join(bytes(p.cpu().tolist()) for p in parts))

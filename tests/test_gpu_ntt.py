@@ -171,3 +171,46 @@ def test_host_pointer_variant_and_errors():
     assert ei.value.code == 5
     with pytest.raises(RonkPanic):   # composite modulus
         c.call("ronk_ntt_u64", 100, 7, dev(a).data_ptr(), 2, 1, 0)
+
+
+def test_distributed_building_blocks():
+    """ronk_field_powers_u64 and ronk_ntt_strided_small_u64 (cross-rank butterflies) vs the oracle."""
+    import torch
+    c = ctx()
+    w = oracle.root_of_unity(GL, 1 << 20)
+    for n, scale in ((1, 1), (5, 3), (4097, 12345678901234567)):
+        out = torch.empty(n, dtype=torch.int64, device="cuda")
+        c.call("ronk_field_powers_u64", GL, w, scale, out.data_ptr(), n)
+        exp = [oracle.mul(GL, scale, oracle.pow_(GL, w, i)) for i in range(n)]
+        assert list(host(out)) == exp
+    for log_g in (1, 2, 3, 4):
+        G, stride, count = 1 << log_g, 37, 29
+        a = oracle.splitmix(GL, log_g, G * stride)
+        d = dev(a)
+        c.call("ronk_ntt_strided_small_u64", GL, 7, d.data_ptr(), log_g, stride, count, 0)
+        got = host(d)
+        exp = a.copy()
+        for k in range(count):
+            exp[k:k + G * stride:stride] = oracle.fft(GL, a[k:k + G * stride:stride].copy())
+        assert np.array_equal(got, exp)
+        c.call("ronk_ntt_strided_small_u64", GL, 7, d.data_ptr(), log_g, stride, count, 1)
+        assert np.array_equal(host(d), a)
+
+
+def test_distributed_transform_single_rank_group():
+    """ntt_distributed / msm_distributed with a 1-rank NCCL group: the whole code path on one GPU."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from ronkathon_b200 import dist as rd
+    c = ctx()
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29617")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        ops_ = rd.LocalOps(c)
+        a = oracle.splitmix(GL, 42, 1 << 14)
+        out = rd.ntt_distributed(ops_, dev(a), 14)
+        assert np.array_equal(host(rd.gather_distributed_output(out, 14)), oracle.ntt_fast(GL, a))
+    finally:
+        dist.destroy_process_group()
