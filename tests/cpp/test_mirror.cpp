@@ -1,0 +1,80 @@
+// test_mirror.cpp — the reference's own unit tests for the hot path, restated against the C++ host
+// mirror (include/ronk_b200.hpp).  Needs a B200; built by __graft_entry__.build(), run by
+// tests/test_gpu_cpp_mirror.py.  Cites the reference tests each block follows.
+#include <cstdio>
+#include <cstdlib>
+
+#include "ronk_b200.hpp"
+
+using namespace ronk;
+
+static int failures = 0;
+#define CHECK(cond)                                                      \
+  do {                                                                   \
+    if (!(cond)) { std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); failures++; } \
+  } while (0)
+template <class Fn>
+static bool panics(Fn fn) {
+  try { fn(); } catch (const Panic&) { return true; }
+  return false;
+}
+template <class F>
+static std::vector<F> vec(std::initializer_list<uint64_t> l) {
+  std::vector<F> v;
+  for (auto x : l) v.emplace_back(x);
+  return v;
+}
+
+int main() {
+  using B = PlutoBaseField;
+  using S = PlutoScalarField;
+  // src/algebra/field/prime/arithmetic.rs:80-216
+  CHECK(S(12) + S(5) == S(0)); CHECK(B(60) + B(60) == B(19));
+  CHECK(S(5) - S(12) == S(10)); CHECK(B(40) - B(61) == B(80));
+  CHECK(S(10) * S(10) == S(15)); CHECK(B(40) * B(61) == B(16));
+  CHECK(S(12).pow(5) == S(3)); CHECK(B(25).pow(25) == B(1)); CHECK(B(0).pow(0) == B(1));
+  CHECK(*S(12).inverse() == S(10)); CHECK(*B(61).inverse() == B(53)); CHECK(!B(0).inverse().has_value());
+  CHECK(B(15) / B(2) == B(58));
+  CHECK(panics([] { (void)(B(1) / B(0)); }));
+  // src/algebra/field/prime/mod.rs:297-314, :386-391
+  CHECK(B::PRIMITIVE_ELEMENT() == B(2)); CHECK(S::PRIMITIVE_ELEMENT() == S(14));
+  CHECK(panics([] { (void)S::primitive_root_of_unity(3); }));
+  // src/polynomial/tests.rs
+  Polynomial<Monomial, B> poly(vec<B>({1, 2, 3, 4}));
+  CHECK(poly.evaluate(B(2)) == B(49));
+  CHECK(poly.dft().coefficients == vec<B>({10, 79, 99, 18}));
+  CHECK(poly.fft().coefficients == vec<B>({10, 79, 99, 18}));
+  CHECK(poly.fft().ifft() == poly);
+  CHECK(poly.dft().evaluate(B(2)) == B(49));
+  CHECK(poly.degree() == 3); CHECK(poly.leading_coefficient() == B(4));
+  CHECK(panics([] { (void)Polynomial<Monomial, B>(vec<B>({1, 2, 3})).dft(); }));
+  // src/polynomial/arithmetic.rs:194-371
+  Polynomial<Monomial, B> a(vec<B>({1, 2, 3, 4})), b(vec<B>({5, 6, 7, 8, 9}));
+  CHECK((b + a).coefficients == vec<B>({6, 8, 10, 12, 9}));
+  CHECK((a * b).coefficients == vec<B>({5, 16, 34, 60, 70, 70, 59, 36}));
+  CHECK((b / a).coefficients == vec<B>({95, 78, 0, 0, 0}));
+  CHECK((b % a).coefficients == vec<B>({11, 41, 71, 0, 0}));
+  // 64-bit instantiation (SURVEY §8c golden NTT8)
+  using G = GoldilocksField;
+  Polynomial<Monomial, G> g8(vec<G>({1, 2, 3, 4, 5, 6, 7, 8}));
+  auto X = g8.fft();
+  CHECK(X.coefficients[0] == G(36)); CHECK(X.coefficients[1] == G(18445622567621360637ULL));
+  CHECK(X.coefficients[7] == G(1121501793223676ULL)); CHECK(X.ifft() == g8);
+  CHECK(G::primitive_root_of_unity(1ULL << 32) == G(1753635133440165772ULL));
+  // src/curve/pluto_curve.rs:90-170, src/kzg/tests.rs
+  AffinePoint g = G1_GENERATOR();
+  AffinePoint two_g = g + g;
+  CHECK((two_g.raw == std::array<uint8_t, 4>{68, 0, 74, 0}));
+  CHECK(((g * S(16)).raw == std::array<uint8_t, 4>{1, 0, 99, 0}));
+  CHECK((g + (-g)).is_infinity());
+  CHECK(panics([] { (void)AffinePoint::make(36, 0, 0, 81); }));
+  auto srs = kzg::setup();
+  CHECK(srs.first.size() == 7 && srs.second.size() == 2);
+  CHECK((srs.first[3].raw == std::array<uint8_t, 4>{18, 0, 49, 0}));
+  CHECK(kzg::commit(vec<S>({11, 11, 11, 1}), srs.first).is_infinity());
+  CHECK((kzg::commit(vec<S>({7, 16, 1, 11, 1}), srs.first).raw == std::array<uint8_t, 4>{32, 0, 59, 0}));
+  CHECK((kzg::open(vec<S>({11, 11, 11, 1}), S(4), srs.first).raw == std::array<uint8_t, 4>{26, 0, 45, 0}));
+  CHECK(panics([&] { (void)kzg::commit(std::vector<S>(8, S(1)), srs.first); }));
+  std::printf(failures ? "%d FAILURES\n" : "cpp mirror ok\n", failures);
+  return failures ? 1 : 0;
+}
