@@ -133,3 +133,23 @@ def test_evaluate_vs_oracle(gold64):
         assert list(got) == exp, d
         if 0 < d <= 300:  # the reference's literal O(D²) form gives the same values
             assert exp == [oracle.poly_eval(GL, co, int(x)) for x in xs]
+
+
+def test_reed_solomon_encode_and_shamir_next_rows(kats):
+    """§8f: RS encode (codes/reed_solomon.rs:136-154, P = 127) and Shamir-style multi-point evaluate."""
+    from ronkathon_b200 import PrimeField, codes
+    ctx()
+    r = kats["reed_solomon"]
+    F = PrimeField(r["p"])
+    cw = codes.rs_encode(r["msg"], r["n"], F)
+    assert [x.value for x, _ in cw] == r["x"] and [y.value for _, y in cw] == r["y"]
+    xs, ys = oracle.rs_encode(127, [1, 2, 3], 7)                      # encode_larger_size: N = 7
+    cw7 = codes.rs_encode([1, 2, 3], 7, F)
+    assert [x.value for x, _ in cw7] == list(xs) and [y.value for _, y in cw7] == list(ys)
+    from ronkathon_b200 import GoldilocksField
+    msg = [int(v) for v in oracle.splitmix(GL, 3, 100)]
+    xs, ys = oracle.rs_encode(GL, msg, 256)
+    cw = codes.rs_encode(msg, 256, GoldilocksField)                    # power of two → NTT path
+    assert [x.value for x, _ in cw] == list(xs) and [y.value for _, y in cw] == list(ys)
+    shares = codes.shamir_shares([11, 5, 7, 3], 9, PrimeField(101))
+    assert [(x, y.value) for x, y in shares] == [(x, oracle.poly_eval(101, [11, 5, 7, 3], x)) for x in range(1, 10)]
