@@ -72,12 +72,9 @@ static int build_plan(ronk_ctx* ctx, const F& f, u64 p, u64 g, u32 log_n, NttPla
 template <class F, int MODE, bool INV, int NTHR, int MINB>
 static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
   const size_t smem = ((size_t)1 << A.tile_log) * sizeof(u64) + ((size_t)1 << A.log_m) * sizeof(u64) + 16;
-  static bool attr_done = false;  // one device per process in practice; re-set is harmless
-  if (!attr_done) {
-    RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_tile_kernel<F, MODE, INV, NTHR, MINB>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_done = true;
-  }
+  // set on every launch: the attribute is per device, and several contexts may live in one process
+  RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_tile_kernel<F, MODE, INV, NTHR, MINB>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   {
     LaunchScope ls(ctx, name);
     ntt_tile_kernel<F, MODE, INV, NTHR, MINB><<<tiles, NTHR, smem, ctx->stream>>>(f, A);
@@ -88,12 +85,8 @@ static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 ti
 template <class F, int MODE, bool INV>
 static int launch_pipe(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
   const size_t smem = ((size_t)2 << A.tile_log) * sizeof(u64) + ((size_t)1 << A.log_m) * sizeof(u64) + 16;
-  static bool attr_done = false;
-  if (!attr_done) {
-    RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_pipe_kernel<F, MODE, INV, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        226 * 1024));
-    attr_done = true;
-  }
+  RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_pipe_kernel<F, MODE, INV, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      226 * 1024));
   const u32 grid = tiles < (u32)ctx->sm_count ? tiles : (u32)ctx->sm_count;
   {
     LaunchScope ls(ctx, name);

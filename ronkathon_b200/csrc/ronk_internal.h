@@ -79,6 +79,7 @@ struct LaunchScope {
   cudaEvent_t start = nullptr, stop = nullptr;
   const char* name;
   LaunchScope(ronk_ctx* c, const char* n) : ctx(c), on(c->prof), name(n) {
+    cudaSetDevice(ctx->device);  // contexts for several devices may coexist in one process
     ctx->launches++;
     if (on) {
       cudaEventCreate(&start);
