@@ -79,22 +79,38 @@ struct GoldilocksField {
   //   x = (Y - r3) + W = sub(sub(Y, r3), p - W) with p - W = (~r1 : 1) — two canonical subs.
   static __device__ __forceinline__ u64 reduce_words(u32 r0, u32 r1, u32 r2, u32 r3) {
     u32 z0, z1;
-    asm("{\n\t.reg .u64 y;\n\t.reg .u32 y0, y1, m, n1;\n\t"
+    // second step: t - (p - W) ≡ t + (r1 : 0xFFFFFFFF) (mod 2^64), and it borrows exactly when this
+    // addition does NOT carry; m = carry - 1 is then the EPS mask of the "+p" correction.
+    asm("{\n\t.reg .u64 y;\n\t.reg .u32 y0, y1, m;\n\t"
         "mad.wide.u32 y, %4, 0xFFFFFFFF, %6;\n\t"
         "mov.b64 {y0, y1}, y;\n\t"
-        "sub.cc.u32 %0, y0, %5;\n\t"        // Y - r3
+        "sub.cc.u32 %0, y0, %5;\n\t"        // t = Y - r3
         "subc.cc.u32 %1, y1, 0;\n\t"
         "subc.u32 m, 0, 0;\n\t"
         "sub.cc.u32 %0, %0, m;\n\t"
         "subc.u32 %1, %1, 0;\n\t"
-        "not.b32 n1, %3;\n\t"               // p - W = (~r1 : 1)
-        "sub.cc.u32 %0, %0, 1;\n\t"
-        "subc.cc.u32 %1, %1, n1;\n\t"
-        "subc.u32 m, 0, 0;\n\t"
+        "add.cc.u32 %0, %0, 0xFFFFFFFF;\n\t" // t + (r1 : 0xFFFFFFFF)
+        "addc.cc.u32 %1, %1, %3;\n\t"
+        "addc.u32 m, 0xFFFFFFFF, 0;\n\t"     // carry - 1
         "sub.cc.u32 %0, %0, m;\n\t"
         "subc.u32 %1, %1, 0;\n\t}"
         : "=&r"(z0), "=&r"(z1)
         : "r"(r0), "r"(r1), "r"(r2), "r"(r3), "l"((u64)r0));
+    return ((u64)z1 << 32) | z0;
+  }
+  // three-word form (r3 = 0): x = Y + W only
+  static __device__ __forceinline__ u64 reduce_words3(u32 r0, u32 r1, u32 r2) {
+    u32 z0, z1;
+    asm("{\n\t.reg .u64 y;\n\t.reg .u32 y0, y1, m;\n\t"
+        "mad.wide.u32 y, %4, 0xFFFFFFFF, %5;\n\t"
+        "mov.b64 {y0, y1}, y;\n\t"
+        "add.cc.u32 %0, y0, 0xFFFFFFFF;\n\t"
+        "addc.cc.u32 %1, y1, %3;\n\t"
+        "addc.u32 m, 0xFFFFFFFF, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(z0), "=&r"(z1)
+        : "r"(r0), "r"(r1), "r"(r2), "l"((u64)r0));
     return ((u64)z1 << 32) | z0;
   }
   __device__ __forceinline__ u64 reduce128(u64 lo, u64 hi) const {
@@ -142,7 +158,7 @@ struct GoldilocksField {
         const u64 hi = (u64)a1 * (u64)(1u << s) + (lo >> 32);   // no overflow: < 2^(32+s)
         y0 = (u32)lo; y1 = (u32)hi; y2 = (u32)(hi >> 32);
       }
-      if constexpr (S < 32) return reduce_words(y0, y1, y2, 0u);
+      if constexpr (S < 32) return reduce_words3(y0, y1, y2);
       else if constexpr (S < 64) return reduce_words(0u, y0, y1, y2);
       else {
         // y·B² = y0·B² + y1·B³ + y2·B⁴ ≡ y0·EPS - (y2:y1);  y0·EPS < p and (y2:y1) < 2^63 < p
