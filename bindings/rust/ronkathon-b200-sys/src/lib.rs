@@ -51,6 +51,8 @@ extern "C" {
   // Polynomial::fft / ifft / dft (src/polynomial/mod.rs:240-323, :430-484)
   pub fn ronk_ntt_u64(ctx: *mut ronk_ctx, p: u64, g: u64, data: *mut u64, log_n: u32, batch: u32, inverse: c_int) -> c_int;
   pub fn ronk_ntt_u64_host(ctx: *mut ronk_ctx, p: u64, g: u64, data: *mut u64, log_n: u32, batch: u32, inverse: c_int) -> c_int;
+  pub fn ronk_ntt_u64_host_submit(ctx: *mut ronk_ctx, p: u64, g: u64, data: *mut u64, log_n: u32, batch: u32, inverse: c_int, slot: c_int) -> c_int;
+  pub fn ronk_ntt_u64_host_wait(ctx: *mut ronk_ctx, slot: c_int) -> c_int;
   pub fn ronk_ntt_mul_u64(ctx: *mut ronk_ctx, p: u64, g: u64, data: *mut u64, mul: *const u64, log_n: u32, batch: u32) -> c_int;
   pub fn ronk_ntt_strided_small_u64(ctx: *mut ronk_ctx, p: u64, g: u64, data: *mut u64, log_g: u32, stride: usize, count: usize, inverse: c_int) -> c_int;
   pub fn ronk_dft_u64(ctx: *mut ronk_ctx, p: u64, g: u64, input: *const u64, n: u64, out: *mut u64) -> c_int;

@@ -99,6 +99,13 @@ int ronk_field_pow_u64_host(ronk_ctx *ctx, uint64_t p, const uint64_t *a, uint64
  * RONK_EINVAL if 2^log_n does not divide p-1; RONK_EUNSUPPORTED if log_n > 26. */
 int ronk_ntt_u64(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *data, uint32_t log_n, uint32_t batch, int inverse);
 int ronk_ntt_u64_host(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *host_data, uint32_t log_n, uint32_t batch, int inverse);
+/* Pipelined host-buffer transforms: `submit` enqueues H2D → transform → D2H for `host_data`
+ * (pinned memory recommended) on slot 0, 1 or 2 and returns at once; `wait` blocks until that
+ * slot's result is back in host memory.  With the slots in flight the PCIe upload of one step, the
+ * kernels of the previous and the download of the one before overlap (PCIe is full duplex).
+ * ronk_ntt_u64_host(…) == submit(slot 0) + wait(0). */
+int ronk_ntt_u64_host_submit(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *host_data, uint32_t log_n, uint32_t batch, int inverse, int slot);
+int ronk_ntt_u64_host_wait(ronk_ctx *ctx, int slot);
 /* Forward transform whose last stage also multiplies point-wise by `mul` (same shape, natural
  * order): data[k] = NTT(data)[k] * mul[k].  The fused form of the evaluate→multiply step. */
 int ronk_ntt_mul_u64(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *data, const uint64_t *mul, uint32_t log_n, uint32_t batch);

@@ -45,6 +45,8 @@ SIGNATURES = {
     "ronk_field_pow_u64_host": (i32, [vp, u64, vp, u64, vp, sz]),
     "ronk_ntt_u64": (i32, [vp, u64, u64, vp, u32, u32, i32]),
     "ronk_ntt_u64_host": (i32, [vp, u64, u64, vp, u32, u32, i32]),
+    "ronk_ntt_u64_host_submit": (i32, [vp, u64, u64, vp, u32, u32, i32, i32]),
+    "ronk_ntt_u64_host_wait": (i32, [vp, i32]),
     "ronk_ntt_mul_u64": (i32, [vp, u64, u64, vp, vp, u32, u32]),
     "ronk_field_powers_u64": (i32, [vp, u64, u64, u64, vp, sz]),
     "ronk_ntt_strided_small_u64": (i32, [vp, u64, u64, vp, u32, sz, sz, i32]),

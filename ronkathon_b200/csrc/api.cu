@@ -56,6 +56,14 @@ int ronk_ctx_destroy(ronk_ctx* ctx) {
     if (p.tw_hi_inv) cudaFree(p.tw_hi_inv);
   }
   for (auto& r : ctx->prof_log) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
+  for (int i = 0; i < ronk_ctx::kSlots; i++) {
+    if (ctx->slot_buf[i]) cudaFree(ctx->slot_buf[i]);
+    if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+    if (ctx->ev_compute[i]) cudaEventDestroy(ctx->ev_compute[i]);
+    if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
+  }
+  if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws2) cudaFree(ctx->ws2);
   if (ctx->d_flag) cudaFree(ctx->d_flag);

@@ -203,16 +203,63 @@ extern "C" int ronk_ntt_mul_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t*
   return ntt_device(ctx, p, g, (u64*)data, (const u64*)mul, log_n, batch, 0);
 }
 
-extern "C" int ronk_ntt_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* host_data, uint32_t log_n,
-                                 uint32_t batch, int inverse) {
+static int pipeline_init(ronk_ctx* ctx) {
+  if (ctx->copy_in) return RONK_OK;
+  RONK_CUDA(ctx, cudaSetDevice(ctx->device));
+  RONK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+  RONK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+  for (int i = 0; i < ronk_ctx::kSlots; i++) {
+    RONK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+    RONK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_compute[i], cudaEventDisableTiming));
+    RONK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+  }
+  return RONK_OK;
+}
+
+extern "C" int ronk_ntt_u64_host_wait(ronk_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= ronk_ctx::kSlots) return set_err(ctx, RONK_EINVAL, "bad slot");
+  if (!ctx->slot_pending[slot]) return RONK_OK;
+  RONK_CUDA(ctx, cudaEventSynchronize(ctx->ev_d2h[slot]));
+  ctx->slot_pending[slot] = false;
+  return RONK_OK;
+}
+
+extern "C" int ronk_ntt_u64_host_submit(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* host_data, uint32_t log_n,
+                                        uint32_t batch, int inverse, int slot) {
   if (!ctx || !host_data) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (slot < 0 || slot >= ronk_ctx::kSlots) return set_err(ctx, RONK_EINVAL, "bad slot");
   if (log_n > 26) return set_err(ctx, RONK_EUNSUPPORTED, "log_n > 26 not supported");
   const size_t bytes = ((size_t)batch << log_n) * sizeof(u64);
   if (bytes == 0) return RONK_OK;
-  RONK_TRY(ensure_ws(ctx, &ctx->ws2, &ctx->ws2_bytes, bytes));
-  RONK_CUDA(ctx, cudaMemcpyAsync(ctx->ws2, host_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  RONK_TRY(ntt_device(ctx, p, g, (u64*)ctx->ws2, nullptr, log_n, batch, inverse));
-  RONK_CUDA(ctx, cudaMemcpyAsync(host_data, ctx->ws2, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  RONK_TRY(pipeline_init(ctx));
+  RONK_TRY(ronk_ntt_u64_host_wait(ctx, slot));  // the slot's previous occupant must be home first
+  if (ctx->slot_bytes[slot] < bytes) {
+    if (ctx->slot_buf[slot]) {
+      RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      RONK_CUDA(ctx, cudaFree(ctx->slot_buf[slot]));
+      ctx->slot_buf[slot] = nullptr;
+      ctx->slot_bytes[slot] = 0;
+    }
+    RONK_CUDA(ctx, cudaMalloc(&ctx->slot_buf[slot], bytes));
+    ctx->slot_bytes[slot] = bytes;
+  }
+  u64* dbuf = (u64*)ctx->slot_buf[slot];
+  RONK_CUDA(ctx, cudaMemcpyAsync(dbuf, host_data, bytes, cudaMemcpyHostToDevice, ctx->copy_in));
+  RONK_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_in));
+  RONK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
+  RONK_TRY(ntt_device(ctx, p, g, dbuf, nullptr, log_n, batch, inverse));
+  RONK_CUDA(ctx, cudaEventRecord(ctx->ev_compute[slot], ctx->stream));
+  RONK_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_compute[slot], 0));
+  RONK_CUDA(ctx, cudaMemcpyAsync(host_data, dbuf, bytes, cudaMemcpyDeviceToHost, ctx->copy_out));
+  RONK_CUDA(ctx, cudaEventRecord(ctx->ev_d2h[slot], ctx->copy_out));
+  ctx->slot_pending[slot] = true;
   return RONK_OK;
+}
+
+extern "C" int ronk_ntt_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* host_data, uint32_t log_n,
+                                 uint32_t batch, int inverse) {
+  if (!ctx || !host_data) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (((size_t)batch << log_n) == 0) return RONK_OK;
+  RONK_TRY(ronk_ntt_u64_host_submit(ctx, p, g, host_data, log_n, batch, inverse, 0));
+  return ronk_ntt_u64_host_wait(ctx, 0);
 }

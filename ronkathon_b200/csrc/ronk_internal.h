@@ -47,6 +47,13 @@ struct ronk_ctx {
   size_t ws_bytes = 0;
   void* ws2 = nullptr;  // second scratch buffer (poly_mul)
   size_t ws2_bytes = 0;
+  // two-slot host pipeline (ronk_ntt_u64_host_submit / _wait)
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  static constexpr int kSlots = 3;
+  void* slot_buf[kSlots] = {};
+  size_t slot_bytes[kSlots] = {};
+  cudaEvent_t ev_h2d[kSlots] = {}, ev_compute[kSlots] = {}, ev_d2h[kSlots] = {};
+  bool slot_pending[kSlots] = {};
   int* d_flag = nullptr;  // device error flag
   int* h_flag = nullptr;  // pinned host mirror
 };

@@ -214,3 +214,23 @@ def test_distributed_transform_single_rank_group():
         assert np.array_equal(host(rd.gather_distributed_output(out, 14)), oracle.ntt_fast(GL, a))
     finally:
         dist.destroy_process_group()
+
+
+def test_pipelined_host_submit_wait():
+    """ronk_ntt_u64_host_submit/_wait: several host buffers in flight over the two slots."""
+    import torch
+    c = ctx()
+    lg = 18
+    bufs, exps = [], []
+    for i in range(5):
+        a = oracle.splitmix(GL, 900 + i, 1 << lg)
+        t = torch.from_numpy(a.copy().view(np.int64)).pin_memory()
+        bufs.append(t); exps.append(oracle.ntt_fast(GL, a))
+    for i, t in enumerate(bufs):
+        c.call("ronk_ntt_u64_host_submit", GL, 7, t.data_ptr(), lg, 1, 0, i & 1)
+        if i >= 1:
+            c.call("ronk_ntt_u64_host_wait", (i - 1) & 1)
+    c.call("ronk_ntt_u64_host_wait", (len(bufs) - 1) & 1)
+    for t, e in zip(bufs, exps):
+        assert np.array_equal(t.numpy().view(np.uint64), e)
+    c.call("ronk_ntt_u64_host_wait", 0)  # idempotent on an idle slot
