@@ -64,13 +64,21 @@ struct GoldilocksField {
   __device__ __forceinline__ u64 sub(u64 a, u64 b) const {
     return sub_words((u32)a, (u32)(a >> 32), (u32)b, (u32)(b >> 32));
   }
+  // a + b = a - (p - b) ≡ a + (b + EPS) (mod 2^64); that subtraction borrows exactly when this addition
+  // does NOT carry (then +p, i.e. -EPS).  b + EPS < 2^64 because b < p.  Add-family carries only.
   __device__ __forceinline__ u64 add(u64 a, u64 b) const {
-    u32 n0, n1;
-    asm("sub.cc.u32 %0, 1, %2;\n\t"
-        "subc.u32 %1, 0xFFFFFFFF, %3;"
-        : "=&r"(n0), "=&r"(n1)
-        : "r"((u32)b), "r"((u32)(b >> 32)));   // (n1:n0) = p - b
-    return sub_words((u32)a, (u32)(a >> 32), n0, n1);
+    u32 s0, s1;
+    asm("{\n\t.reg .u32 t0, t1, m;\n\t"
+        "add.cc.u32 t0, %4, 0xFFFFFFFF;\n\t"
+        "addc.u32 t1, %5, 0;\n\t"
+        "add.cc.u32 %0, %2, t0;\n\t"
+        "addc.cc.u32 %1, %3, t1;\n\t"
+        "addc.u32 m, 0xFFFFFFFF, 0;\n\t"      // carry - 1: 0 or 0xFFFFFFFF (= EPS·borrow)
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(s0), "=&r"(s1)
+        : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return ((u64)s1 << 32) | s0;
   }
   __device__ __forceinline__ u64 neg(u64 a) const { return a ? GL_P - a : 0; }
 

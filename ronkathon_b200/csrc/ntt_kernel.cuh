@@ -103,15 +103,17 @@ RONK_DEV void ntt_round(const F& f, u64* smem, const u64* tw, const NttTileArgs&
   const u32 e0 = ((t >> wb) << (wb + 4)) | (t & lowmask);
   // The swizzle is XOR-linear and e0 has no bits inside the window, so the 16 addresses are
   // swz(e0) ^ swz(q << wb): walk q in Gray-code order and pay one XOR per access.
-  const u32 base = swz(e0);
-  const u32 g0 = swz(1u << wb), g1 = swz(2u << wb), g2 = swz(4u << wb), g3 = swz(8u << wb);
+  // byte offsets, so each access is a plain LDS/STS [reg] with no index→address arithmetic
+  const u32 base = swz(e0) << 3;
+  const u32 g0 = swz(1u << wb) << 3, g1 = swz(2u << wb) << 3, g2 = swz(4u << wb) << 3, g3 = swz(8u << wb) << 3;
+  char* const sbytes = reinterpret_cast<char*>(smem);
   u64 x[16];
   {
     u32 addr = base;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
       const int q = i ^ (i >> 1);
-      x[q] = smem[addr];
+      x[q] = *reinterpret_cast<const u64*>(sbytes + addr);
       const int flip = (i + 1) & -(i + 1);  // Gray code: bit index = ctz(i + 1)
       addr ^= (flip == 1) ? g0 : (flip == 2) ? g1 : (flip == 4) ? g2 : (flip == 8) ? g3 : 0u;
     }
@@ -134,7 +136,7 @@ RONK_DEV void ntt_round(const F& f, u64* smem, const u64* tw, const NttTileArgs&
 #pragma unroll
     for (int i = 0; i < 16; i++) {
       const int q = i ^ (i >> 1);
-      smem[addr] = x[q];
+      *reinterpret_cast<u64*>(sbytes + addr) = x[q];
       const int flip = (i + 1) & -(i + 1);
       addr ^= (flip == 1) ? g0 : (flip == 2) ? g1 : (flip == 4) ? g2 : (flip == 8) ? g3 : 0u;
     }
