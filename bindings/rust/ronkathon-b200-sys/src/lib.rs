@@ -55,6 +55,11 @@ extern "C" {
   pub fn ronk_ntt_u64_host_wait(ctx: *mut ronk_ctx, slot: c_int) -> c_int;
   pub fn ronk_ntt_mul_u64(ctx: *mut ronk_ctx, p: u64, g: u64, data: *mut u64, mul: *const u64, log_n: u32, batch: u32) -> c_int;
   pub fn ronk_ntt_strided_small_u64(ctx: *mut ronk_ctx, p: u64, g: u64, data: *mut u64, log_g: u32, stride: usize, count: usize, inverse: c_int) -> c_int;
+  pub fn ronk_ntt_cross_rank_fused_u64(ctx: *mut ronk_ctx, p: u64, g: u64, peer_bufs: *const *const u64, log_g: u32, rank: u32, log_n: u32, out: *mut u64) -> c_int;
+  pub fn ronk_ipc_export(ctx: *mut ronk_ctx, dptr: *const c_void, handle: *mut u8) -> c_int;
+  pub fn ronk_ipc_open(ctx: *mut ronk_ctx, handle: *const u8, dptr: *mut *mut c_void) -> c_int;
+  pub fn ronk_ipc_close(ctx: *mut ronk_ctx, dptr: *mut c_void) -> c_int;
+  pub fn ronk_memcpy_d2d(ctx: *mut ronk_ctx, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
   pub fn ronk_dft_u64(ctx: *mut ronk_ctx, p: u64, g: u64, input: *const u64, n: u64, out: *mut u64) -> c_int;
   pub fn ronk_dft_u64_host(ctx: *mut ronk_ctx, p: u64, g: u64, input: *const u64, n: u64, out: *mut u64) -> c_int;
 

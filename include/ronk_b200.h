@@ -122,6 +122,21 @@ int ronk_field_powers_u64(ronk_ctx *ctx, uint64_t p, uint64_t base, uint64_t sca
  * ronk_ntt_u64 (ω_G = g^((p-1)/G)); inverse applies G^-1. */
 int ronk_ntt_strided_small_u64(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *data, uint32_t log_g, size_t stride, size_t count, int inverse);
 
+/* Peer-memory fused form of the same stage: ONE kernel per rank that loads the peers' local
+ * transforms directly over NVLink (P2P loads through CUDA-IPC-mapped pointers), applies the twiddle
+ * column ω_n^(r'·k') on the fly and runs the G-point cross-rank butterflies — twiddle multiply,
+ * all-to-all and butterflies in a single launch, no staging buffer.  `peer_bufs[r']` (host array of
+ * G device pointers, entry `rank` being this rank's own buffer) each hold that rank's n/G-point
+ * local transform Y_r'; `out` (n/G words) receives X[(rank·m/G + k'') + m·q] at q·(m/G) + k''.
+ * Callers must make sure every rank's Y is complete before the launch (host barrier). */
+int ronk_ntt_cross_rank_fused_u64(ronk_ctx *ctx, uint64_t p, uint64_t g, const uint64_t *const *peer_bufs, uint32_t log_g, uint32_t rank, uint32_t log_n, uint64_t *out);
+/* CUDA-IPC plumbing for the above: export a handle for a buffer obtained from ronk_dev_alloc, open a
+ * peer's handle (enables peer access), close it again; and a device-to-device copy. */
+int ronk_ipc_export(ronk_ctx *ctx, const void *dptr, uint8_t handle[64]);
+int ronk_ipc_open(ronk_ctx *ctx, const uint8_t handle[64], void **dptr);
+int ronk_ipc_close(ronk_ctx *ctx, void *dptr);
+int ronk_memcpy_d2d(ronk_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);
+
 /* ---- Polynomial<Monomial, F, D> ----------------------------------------------------------- */
 /* Mul — src/polynomial/arithmetic.rs:97-119.  c has da+db-1 coefficients (no trimming).
  * NTT path (pad → NTT, NTT∘pointwise → iNTT) when a power of two ≥ da+db-1 divides p-1 and

@@ -50,6 +50,11 @@ SIGNATURES = {
     "ronk_ntt_mul_u64": (i32, [vp, u64, u64, vp, vp, u32, u32]),
     "ronk_field_powers_u64": (i32, [vp, u64, u64, u64, vp, sz]),
     "ronk_ntt_strided_small_u64": (i32, [vp, u64, u64, vp, u32, sz, sz, i32]),
+    "ronk_ntt_cross_rank_fused_u64": (i32, [vp, u64, u64, vp, u32, u32, u32, vp]),
+    "ronk_ipc_export": (i32, [vp, vp, vp]),
+    "ronk_ipc_open": (i32, [vp, vp, C.POINTER(vp)]),
+    "ronk_ipc_close": (i32, [vp, vp]),
+    "ronk_memcpy_d2d": (i32, [vp, vp, vp, sz]),
     "ronk_dft_u64": (i32, [vp, u64, u64, vp, u64, vp]),
     "ronk_dft_u64_host": (i32, [vp, u64, u64, vp, u64, vp]),
     "ronk_poly_mul_u64": (i32, [vp, u64, u64, vp, sz, vp, sz, vp]),

@@ -137,4 +137,36 @@ int ronk_memcpy_d2h(ronk_ctx* ctx, void* dst_host, const void* src_dev, size_t b
   return RONK_OK;
 }
 
+int ronk_memcpy_d2d(ronk_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes) {
+  if (!ctx) return RONK_EINVAL;
+  RONK_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return RONK_OK;
+}
+
+int ronk_ipc_export(ronk_ctx* ctx, const void* dptr, uint8_t handle[64]) {
+  if (!ctx || !dptr || !handle) return set_err(ctx, RONK_EINVAL, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  RONK_CUDA(ctx, cudaSetDevice(ctx->device));
+  RONK_CUDA(ctx, cudaIpcGetMemHandle(&h, const_cast<void*>(dptr)));
+  std::memcpy(handle, &h, 64);
+  return RONK_OK;
+}
+
+int ronk_ipc_open(ronk_ctx* ctx, const uint8_t handle[64], void** dptr) {
+  if (!ctx || !dptr || !handle) return set_err(ctx, RONK_EINVAL, "null argument");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  RONK_CUDA(ctx, cudaSetDevice(ctx->device));
+  RONK_CUDA(ctx, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return RONK_OK;
+}
+
+int ronk_ipc_close(ronk_ctx* ctx, void* dptr) {
+  if (!ctx) return RONK_EINVAL;
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  RONK_CUDA(ctx, cudaIpcCloseMemHandle(dptr));
+  return RONK_OK;
+}
+
 }  // extern "C"

@@ -71,6 +71,36 @@ __global__ void strided_dft_kernel(const F f, u64* data, u32 G, size_t stride, s
   }
 }
 
+// Fused cross-rank stage of the distributed transform.  Thread k'' of rank s handles
+// k' = s·blk + k'': it loads Y_r'[k'] from every peer r' (plain ld.global on peer-mapped addresses —
+// NVLink P2P), multiplies by ω_n^(r'·k') = base^r' (base = ω_n^k' from `twbase`), runs the G-point
+// transform and writes X[k' + m·q] to out[q·blk + k''].  O(G²) per k', G ≤ 16.
+struct PeerPtrs {
+  const u64* p[16];
+};
+template <class F>
+__global__ void cross_rank_fused_kernel(const F f, const PeerPtrs peers, const u64* __restrict__ twbase, const u64* wt,
+                                        u64* __restrict__ out, u32 G, size_t blk, u32 rank) {
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < blk; k += step) {
+    const size_t kp = (size_t)rank * blk + k;
+    u64 x[16], y[16];
+    for (u32 r = 0; r < G; r++) x[r] = peers.p[r][kp];   // P2P loads first: all in flight together
+    const u64 base = twbase[k];
+    u64 tw = base;
+    for (u32 r = 1; r < G; r++) {
+      x[r] = f.mul(x[r], tw);
+      tw = f.mul(tw, base);
+    }
+    for (u32 q = 0; q < G; q++) {
+      u64 acc = 0;
+      for (u32 j = 0; j < G; j++) acc = f.add(acc, f.mul(x[j], wt[(j * q) & (G - 1)]));
+      y[q] = acc;
+    }
+    for (u32 q = 0; q < G; q++) out[(size_t)q * blk + k] = y[q];
+  }
+}
+
 __global__ void splitmix_kernel(u64 p, u64 seed, u64* out, size_t n) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -289,6 +319,50 @@ int ronk_ntt_strided_small_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* 
                                                                        (const u64*)ctx->ws2, sc);
   }
   return check_launch(ctx, "strided_dft_kernel");
+}
+
+int ronk_ntt_cross_rank_fused_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t* const* peer_bufs,
+                                  uint32_t log_g, uint32_t rank, uint32_t log_n, uint64_t* out) {
+  if (!ctx || !peer_bufs || !out) return set_err(ctx, RONK_EINVAL, "null argument");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (g == 0 || g >= p) return set_err(ctx, RONK_EINVAL, "generator out of range");
+  if (log_g > 4 || log_g == 0) return set_err(ctx, RONK_EUNSUPPORTED, "group size must be 2..16");
+  if (log_n >= 64 || (p - 1) % ((u64)1 << log_n) != 0)
+    return set_err(ctx, RONK_EINVAL, "n must divide p - 1 (no primitive n-th root of unity)");
+  if (log_n < 2 * log_g) return set_err(ctx, RONK_EINVAL, "transform too small for this group");
+  const u32 G = 1u << log_g;
+  if (rank >= G) return set_err(ctx, RONK_EINVAL, "rank out of range");
+  const size_t m = (size_t)1 << (log_n - log_g), blk = m >> log_g;
+  const u64 wn = h_powmod(g, (p - 1) >> log_n, p);
+  const u64 wg = h_powmod(g, (p - 1) >> log_g, p);
+  // ws2: [ wt: 16 words | twbase: blk words ]
+  RONK_TRY(ensure_ws(ctx, &ctx->ws2, &ctx->ws2_bytes, (16 + blk) * sizeof(u64)));
+  u64* d_wt = (u64*)ctx->ws2;
+  u64* d_tw = d_wt + 16;
+  u64 h_wt[16];
+  for (u32 j = 0; j < 16; j++) h_wt[j] = j < G ? h_powmod(wg, j, p) : 0;
+  RONK_CUDA(ctx, cudaMemcpyAsync(d_wt, h_wt, sizeof(h_wt), cudaMemcpyHostToDevice, ctx->stream));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // h_wt is a stack buffer
+  // twbase[k''] = ω_n^(rank·blk + k'')
+  RONK_TRY(ronk_field_powers_u64(ctx, p, wn, h_powmod(wn, (u64)rank * blk, p), (uint64_t*)d_tw, blk));
+  PeerPtrs pp;
+  for (u32 r = 0; r < 16; r++) pp.p[r] = r < G ? (const u64*)peer_bufs[r] : nullptr;
+  for (u32 r = 0; r < G; r++)
+    if (!pp.p[r]) return set_err(ctx, RONK_EINVAL, "null peer buffer");
+  const int threads = 128;
+  size_t blocks = (blk + threads - 1) / threads;
+  if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
+  if (p == GL_P) {
+    GoldilocksField f;
+    LaunchScope ls(ctx, "ntt_cross_rank_fused");
+    cross_rank_fused_kernel<GoldilocksField><<<(int)blocks, threads, 0, ctx->stream>>>(f, pp, d_tw, d_wt, (u64*)out, G, blk, rank);
+  } else {
+    MontField f;
+    RONK_TRY(make_mont_field(ctx, p, 0, false, &f));
+    LaunchScope ls(ctx, "ntt_cross_rank_fused");
+    cross_rank_fused_kernel<MontField><<<(int)blocks, threads, 0, ctx->stream>>>(f, pp, d_tw, d_wt, (u64*)out, G, blk, rank);
+  }
+  return check_launch(ctx, "cross_rank_fused_kernel");
 }
 
 int ronk_splitmix_fill_u64(ronk_ctx* ctx, uint64_t p, uint64_t seed, uint64_t* out, size_t n) {

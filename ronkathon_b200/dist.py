@@ -128,3 +128,62 @@ def msm_distributed(ops: LocalOps, points_shard, scalars_shard, group=None) -> b
     parts = [torch.empty_like(send) for _ in range(G)]
     dist.all_gather(parts, send, group=group)
     return ops.msm_combine(b"".join(bytes(p.cpu().tolist()) for p in parts))
+
+
+class FusedDistributedNTT:
+    """One 2^log_n-point transform across the group with the exchange FUSED into the final kernel.
+
+    Each rank keeps its local n/G-point transform in an IPC-exported device buffer; after a host
+    barrier every rank launches `ronk_ntt_cross_rank_fused_u64`, whose threads read the peers'
+    blocks directly over NVLink (P2P loads), apply the twiddle column and do the G-point
+    butterflies — no NCCL all-to-all, no staging buffer.  Same output layout as `ntt_distributed`."""
+
+    def __init__(self, ctx, log_n: int, group=None, p: int = GOLDILOCKS, g: int = 7):
+        import ctypes as C
+        self.ctx, self.log_n, self.group, self.p, self.g = ctx, log_n, group, p, g
+        self.G = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.log_g = self.G.bit_length() - 1
+        assert 1 << self.log_g == self.G and self.G >= 2
+        self.m = (1 << log_n) // self.G
+        self.buf = _lib.vp()
+        ctx.call("ronk_dev_alloc", C.byref(self.buf), self.m * 8)
+        handle = (C.c_uint8 * 64)()
+        ctx.call("ronk_ipc_export", self.buf, C.cast(handle, _lib.vp))
+        handles = [None] * self.G
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.peers = (C.c_void_p * self.G)()
+        self._opened = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.peers[r] = self.buf.value
+            else:
+                ptr = _lib.vp()
+                hb = (C.c_uint8 * 64).from_buffer_copy(h)
+                ctx.call("ronk_ipc_open", C.cast(hb, _lib.vp), C.byref(ptr))
+                self.peers[r] = ptr.value
+                self._opened.append(ptr)
+
+    def run(self, local, out=None):
+        """`local`: this rank's a[rank::G] (CUDA int64 tensor, m words). Returns the block-cyclic output tensor."""
+        import ctypes as C
+        assert local.numel() == self.m
+        if out is None:
+            out = torch.empty_like(local)
+        self.ctx.call("ronk_memcpy_d2d", self.buf, _lib._ptr(local), self.m * 8)
+        self.ctx.call("ronk_ntt_u64", self.p, self.g, self.buf, self.log_n - self.log_g, 1, 0)
+        self.ctx.sync()
+        dist.barrier(group=self.group)          # every rank's Y_r is complete and visible
+        self.ctx.call("ronk_ntt_cross_rank_fused_u64", self.p, self.g, C.cast(self.peers, _lib.vp), self.log_g,
+                      self.rank, self.log_n, _lib._ptr(out))
+        self.ctx.sync()
+        dist.barrier(group=self.group)          # peers are done reading before anyone overwrites its buffer
+        return out
+
+    def close(self):
+        for ptr in self._opened:
+            self.ctx.call("ronk_ipc_close", ptr)
+        self._opened = []
+        if self.buf:
+            self.ctx.call("ronk_dev_free", self.buf)
+            self.buf = None

@@ -44,6 +44,13 @@ def main():
     full = ops.to_host(rd.gather_distributed_output(out, lg))
     res["dist_ntt_2_20_bit_exact"] = bool(np.array_equal(full, oracle.ntt_fast(GL, a)))
 
+    # (1b) the same transform with the exchange fused into the final kernel (P2P loads over NVLink)
+    fused = rd.FusedDistributedNTT(ctx, lg)
+    out_f = fused.run(ops.to_device(a[rank::world].copy(), dev))
+    full_f = ops.to_host(rd.gather_distributed_output(out_f, lg))
+    res["fused_dist_ntt_2_20_bit_exact"] = bool(np.array_equal(full_f, oracle.ntt_fast(GL, a)))
+    fused.close()
+
     # (2) config-5 shape, reduced batch for the oracle check: 64 × 2^16
     batch, lgb = 64, 16
     data = oracle.splitmix(GL, 7, batch << lgb)
@@ -97,6 +104,10 @@ def main():
         scratch.copy_(locbuf)
         rd.ntt_distributed(lo, scratch, lg)
     res["dist_ntt_2_24_ms"] = timed(one, iters=5)
+    fused24 = rd.FusedDistributedNTT(ctx, lg)
+    outbuf = torch.empty_like(locbuf)
+    res["fused_dist_ntt_2_24_ms"] = timed(lambda: fused24.run(locbuf, outbuf), iters=5)
+    fused24.close()
 
     # MSM 2^20 timing
     P, S = torch.from_numpy(pts[i0:i1].copy()).to(dev), torch.from_numpy(sc[i0:i1].copy()).to(dev)
