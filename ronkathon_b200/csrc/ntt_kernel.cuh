@@ -145,43 +145,55 @@ RONK_DEV void ntt_round(const F& f, u64* smem, const u64* tw, const NttTileArgs&
 
 // ---------------- load phase: HBM → shared ----------------
 // Loads are issued LD_BATCH at a time into registers before any is stored, so the HBM latency of a
-// tile is paid once per batch, not once per element.
+// tile is paid once per batch, not once per element.  nthr is a power of two, so the tile index of
+// the j-th element of a thread is e = tid | (j·nthr): disjoint bit sets.  The swizzle is XOR-linear,
+// hence swz(e) = swz(tid) ^ swz(j·nthr) — one XOR per element with a warp-uniform second term.
 #ifndef RONK_LD_BATCH
 #define RONK_LD_BATCH 8
 #endif
 constexpr int LD_BATCH = RONK_LD_BATCH;
+RONK_DEV u32 ilog2(u32 v) {
+  u32 l = 0;
+  while ((1u << l) < v) l++;
+  return l;
+}
 template <class F, int MODE>
 RONK_DEV void ntt_load_phase(u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
   const u32 T = 1u << A.tile_log;
+  const u32 kk = ilog2(nthr);
   u32 b = 0, sub = tile;
   if (MODE != MODE_SINGLE) {
     b = tile / A.tiles_per_batch;
     sub = tile - b * A.tiles_per_batch;
   }
-  u64 base;
-  if (MODE == MODE_SINGLE) base = (u64)tile << A.tile_log;
-  else if (MODE == MODE_PASS1) base = ((u64)b << A.log_n) + ((u64)sub << A.log_c);
-  else base = ((u64)b << A.log_n) + ((u64)sub << A.tile_log);
-  const u32 cmask = (1u << A.log_c) - 1u;
-  for (u32 e0 = tid; e0 < T; e0 += nthr * LD_BATCH) {
+  // thread part of the global address
+  u64 gaddr_t;
+  if (MODE == MODE_SINGLE) gaddr_t = ((u64)tile << A.tile_log) + tid;
+  else if (MODE == MODE_PASS1)
+    gaddr_t = ((u64)b << A.log_n) + ((u64)sub << A.log_c) + ((u64)(tid >> A.log_c) << A.log_n2) + (tid & ((1u << A.log_c) - 1u));
+  else gaddr_t = ((u64)b << A.log_n) + ((u64)sub << A.tile_log) + tid;
+  const u32 sw_t = swz(tid);
+  const u32 per_thread = T >> kk;  // elements per thread (T ≥ nthr)
+  for (u32 j0 = 0; j0 < per_thread; j0 += LD_BATCH) {
     u64 v[LD_BATCH];
 #pragma unroll
     for (int i = 0; i < LD_BATCH; i++) {
-      const u32 e = e0 + i * nthr;
-      if (MODE == MODE_SINGLE) {
-        const u64 g = base + e;
-        v[i] = (e < T && g < A.total) ? A.src[g] : 0ULL;
-      } else if (MODE == MODE_PASS1) {
-        const u32 j1 = e >> A.log_c, c = e & cmask;
-        v[i] = (e < T) ? A.src[base + ((u64)j1 << A.log_n2) + c] : 0ULL;
-      } else {
-        v[i] = (e < T) ? A.src[base + e] : 0ULL;
+      const u32 gj = (j0 + i) << kk;  // warp-uniform
+      if (j0 + i < per_thread) {
+        if (MODE == MODE_SINGLE) {
+          const u64 g = gaddr_t + gj;
+          v[i] = (g < A.total) ? A.src[g] : 0ULL;
+        } else if (MODE == MODE_PASS1) {
+          v[i] = A.src[gaddr_t + ((u64)(gj >> A.log_c) << A.log_n2)];  // kk ≥ log_c: gj has no column bits
+        } else {
+          v[i] = A.src[gaddr_t + gj];
+        }
       }
     }
 #pragma unroll
     for (int i = 0; i < LD_BATCH; i++) {
-      const u32 e = e0 + i * nthr;
-      if (e < T) smem[swz(e)] = v[i];
+      const u32 gj = (j0 + i) << kk;
+      if (j0 + i < per_thread) smem[sw_t ^ swz(gj)] = v[i];
     }
   }
 }
@@ -219,53 +231,78 @@ RONK_DEV void ntt_round_dispatch(const F& f, u64* smem, const u64* tw, const Ntt
 }
 
 // ---------------- store phase: shared → HBM (un-bit-reverse on the fly) ----------------
+// g = tid | (j·nthr) enumerates the tile in HBM-friendly order; the tile index holding element g is a
+// fixed PERMUTATION OF THE BITS of g (bit-reversal of the transform field, plus the pass-1 chunk
+// shuffle), so e(g) = e(tid) | e(j·nthr) and, the swizzle being XOR-linear,
+// swz(e(g)) = swz(e(tid)) ^ swz(e(j·nthr)): per element one XOR with a warp-uniform term.
+template <int MODE>
+RONK_DEV u32 store_perm(const NttTileArgs& A, u32 g) {
+  if (MODE == MODE_SINGLE) {
+    const u32 M1 = (1u << A.log_m) - 1u;
+    return ((g >> A.log_m) << A.log_m) | bitrev(g & M1, A.log_m);
+  } else if (MODE == MODE_PASS1) {
+    const u32 lc = A.log_c, lc2 = A.log_c2, cl = lc + lc2;
+    const u32 rem = g & ((1u << cl) - 1u);
+    const u32 k1 = ((g >> cl) << lc2) | (rem & ((1u << lc2) - 1u));
+    return (bitrev(k1, A.log_m) << lc) | (rem >> lc2);
+  } else {
+    const u32 lc2 = A.log_c;
+    return (bitrev(g >> lc2, A.log_m) << lc2) | (g & ((1u << lc2) - 1u));
+  }
+}
+
 template <class F, int MODE, bool INV>
 RONK_DEV void ntt_store_phase(const F& f, const u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
   const u32 T = 1u << A.tile_log;
-  const u32 M = 1u << A.log_m;
+  const u32 kk = ilog2(nthr);
+  const u32 per_thread = T >> kk;
   u32 b = 0, sub = tile;
   if (MODE != MODE_SINGLE) {
     b = tile / A.tiles_per_batch;
     sub = tile - b * A.tiles_per_batch;
   }
+  const u32 sw_t = swz(store_perm<MODE>(A, tid));
   if (MODE == MODE_SINGLE) {
-    const u64 base = (u64)tile << A.tile_log;
-    for (u32 g = tid; g < T; g += nthr) {
-      if (base + g >= A.total) continue;
-      const u32 bt = g >> A.log_m, k = g & (M - 1u);
-      const u32 e = (bt << A.log_m) | bitrev(k, A.log_m);
-      u64 v = smem[swz(e)];
+    const u64 base_t = ((u64)tile << A.tile_log) + tid;
+#pragma unroll 4
+    for (u32 j = 0; j < per_thread; j++) {
+      const u32 gj = j << kk;
+      const u64 ga = base_t + gj;
+      if (ga >= A.total) continue;
+      u64 v = smem[sw_t ^ swz(store_perm<MODE>(A, gj))];
       if (A.flags & NTT_FLAG_SCALE) v = f.mul_tw(v, A.scale);
-      if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[base + g]);
-      A.dst[base + g] = v;
+      if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[ga]);
+      A.dst[ga] = v;
     }
   } else if (MODE == MODE_PASS1) {
-    const u32 lc = A.log_c, lc2 = A.log_c2;
-    const u32 chunk_log = lc + lc2;
+    const u32 lc = A.log_c, lc2 = A.log_c2, cl = lc + lc2;
     const u32 nmask = (A.log_n >= 32) ? 0xFFFFFFFFu : ((1u << A.log_n) - 1u);
     const u32 lomask = (1u << A.log_lo) - 1u;
     const u64 base = (u64)b << A.log_n;
-    for (u32 g = tid; g < T; g += nthr) {
-      const u32 k1_blk = g >> chunk_log;
-      const u32 rem = g & ((1u << chunk_log) - 1u);
+#pragma unroll 4
+    for (u32 j = 0; j < per_thread; j++) {
+      const u32 gj = j << kk;
+      const u32 g = tid | gj;
+      const u32 k1_blk = g >> cl;
+      const u32 rem = g & ((1u << cl) - 1u);
       const u32 c = rem >> lc2, k1_in = rem & ((1u << lc2) - 1u);
       const u32 k1 = (k1_blk << lc2) | k1_in;
-      const u32 e = (bitrev(k1, A.log_m) << lc) | c;
       const u32 j2 = (sub << lc) | c;
       u32 ex = j2 * k1;
       if (INV) ex = (0u - ex) & nmask;
       const u64 w = f.mul_tw(ld_tw(A.tw_lo + (ex & lomask)), ld_tw(A.tw_hi + (ex >> A.log_lo)));
-      const u64 v = f.mul_tw(smem[swz(e)], w);
+      const u64 v = f.mul_tw(smem[sw_t ^ swz(store_perm<MODE>(A, gj))], w);
       A.dst[base + ((u64)k1_blk << (A.log_n2 + lc2)) + ((u64)j2 << lc2) + k1_in] = v;
     }
   } else {
     const u32 lc2 = A.log_c;  // pass-2 tile: columns are the C2 adjacent k1 values
-    const u64 base = ((u64)b << A.log_n) + ((u64)sub << lc2);
-    for (u32 g = tid; g < T; g += nthr) {
-      const u32 k2 = g >> lc2, k1_in = g & ((1u << lc2) - 1u);
-      const u32 e = (bitrev(k2, A.log_m) << lc2) | k1_in;
-      const u64 addr = base + k1_in + ((u64)k2 << A.log_n1);
-      u64 v = smem[swz(e)];
+    // address of g: base + k1_in + (k2 << log_n1), additive over the disjoint bit fields of g
+    const u64 addr_t = ((u64)b << A.log_n) + ((u64)sub << lc2) + (tid & ((1u << lc2) - 1u)) + ((u64)(tid >> lc2) << A.log_n1);
+#pragma unroll 8
+    for (u32 j = 0; j < per_thread; j++) {
+      const u32 gj = j << kk;  // kk ≥ lc2: gj carries no k1_in bits
+      const u64 addr = addr_t + ((u64)(gj >> lc2) << A.log_n1);
+      u64 v = smem[sw_t ^ swz(store_perm<MODE>(A, gj))];
       if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[addr]);
       A.dst[addr] = v;
     }
