@@ -309,6 +309,96 @@ RONK_DEV void ntt_store_phase(const F& f, const u64* smem, const NttTileArgs& A,
   }
 }
 
+// ---- previous formulation of the phases (index math per element), kept selectable per mode ----
+template <class F, int MODE>
+RONK_DEV void ntt_load_phase_v0(u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
+  const u32 T = 1u << A.tile_log;
+  u32 b = 0, sub = tile;
+  if (MODE != MODE_SINGLE) {
+    b = tile / A.tiles_per_batch;
+    sub = tile - b * A.tiles_per_batch;
+  }
+  u64 base;
+  if (MODE == MODE_SINGLE) base = (u64)tile << A.tile_log;
+  else if (MODE == MODE_PASS1) base = ((u64)b << A.log_n) + ((u64)sub << A.log_c);
+  else base = ((u64)b << A.log_n) + ((u64)sub << A.tile_log);
+  const u32 cmask = (1u << A.log_c) - 1u;
+  for (u32 e0 = tid; e0 < T; e0 += nthr * LD_BATCH) {
+    u64 v[LD_BATCH];
+#pragma unroll
+    for (int i = 0; i < LD_BATCH; i++) {
+      const u32 e = e0 + i * nthr;
+      if (MODE == MODE_SINGLE) {
+        const u64 g = base + e;
+        v[i] = (e < T && g < A.total) ? A.src[g] : 0ULL;
+      } else if (MODE == MODE_PASS1) {
+        const u32 j1 = e >> A.log_c, c = e & cmask;
+        v[i] = (e < T) ? A.src[base + ((u64)j1 << A.log_n2) + c] : 0ULL;
+      } else {
+        v[i] = (e < T) ? A.src[base + e] : 0ULL;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LD_BATCH; i++) {
+      const u32 e = e0 + i * nthr;
+      if (e < T) smem[swz(e)] = v[i];
+    }
+  }
+}
+
+template <class F, int MODE, bool INV>
+RONK_DEV void ntt_store_phase_v0(const F& f, const u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
+  const u32 T = 1u << A.tile_log;
+  const u32 M = 1u << A.log_m;
+  u32 b = 0, sub = tile;
+  if (MODE != MODE_SINGLE) {
+    b = tile / A.tiles_per_batch;
+    sub = tile - b * A.tiles_per_batch;
+  }
+  if (MODE == MODE_SINGLE) {
+    const u64 base = (u64)tile << A.tile_log;
+    for (u32 g = tid; g < T; g += nthr) {
+      if (base + g >= A.total) continue;
+      const u32 bt = g >> A.log_m, k = g & (M - 1u);
+      const u32 e = (bt << A.log_m) | bitrev(k, A.log_m);
+      u64 v = smem[swz(e)];
+      if (A.flags & NTT_FLAG_SCALE) v = f.mul_tw(v, A.scale);
+      if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[base + g]);
+      A.dst[base + g] = v;
+    }
+  } else if (MODE == MODE_PASS1) {
+    const u32 lc = A.log_c, lc2 = A.log_c2;
+    const u32 chunk_log = lc + lc2;
+    const u32 nmask = (A.log_n >= 32) ? 0xFFFFFFFFu : ((1u << A.log_n) - 1u);
+    const u32 lomask = (1u << A.log_lo) - 1u;
+    const u64 base = (u64)b << A.log_n;
+    for (u32 g = tid; g < T; g += nthr) {
+      const u32 k1_blk = g >> chunk_log;
+      const u32 rem = g & ((1u << chunk_log) - 1u);
+      const u32 c = rem >> lc2, k1_in = rem & ((1u << lc2) - 1u);
+      const u32 k1 = (k1_blk << lc2) | k1_in;
+      const u32 e = (bitrev(k1, A.log_m) << lc) | c;
+      const u32 j2 = (sub << lc) | c;
+      u32 ex = j2 * k1;
+      if (INV) ex = (0u - ex) & nmask;
+      const u64 w = f.mul_tw(ld_tw(A.tw_lo + (ex & lomask)), ld_tw(A.tw_hi + (ex >> A.log_lo)));
+      const u64 v = f.mul_tw(smem[swz(e)], w);
+      A.dst[base + ((u64)k1_blk << (A.log_n2 + lc2)) + ((u64)j2 << lc2) + k1_in] = v;
+    }
+  } else {
+    const u32 lc2 = A.log_c;  // pass-2 tile: columns are the C2 adjacent k1 values
+    const u64 base = ((u64)b << A.log_n) + ((u64)sub << lc2);
+    for (u32 g = tid; g < T; g += nthr) {
+      const u32 k2 = g >> lc2, k1_in = g & ((1u << lc2) - 1u);
+      const u32 e = (bitrev(k2, A.log_m) << lc2) | k1_in;
+      const u64 addr = base + k1_in + ((u64)k2 << A.log_n1);
+      u64 v = smem[swz(e)];
+      if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[addr]);
+      A.dst[addr] = v;
+    }
+  }
+}
+
 // ---------------- launch geometry (host; shared by ntt.cu and the CPU emulator in tests/emu) -------------
 struct NttShape {
   bool two_pass;
@@ -526,7 +616,18 @@ __global__ void __launch_bounds__(NTHR, MINB) ntt_tile_kernel(const F f, const N
     mbar_expect_tx(bar, M * 8u);
     tma_bulk_g2s(tw, A.tw_tile, M * 8u, bar);  // lands while the tile itself is being loaded
   }
-  ntt_load_phase<F, MODE>(smem, A, tile, tid, NTHR);
+  // Which formulation of the load/store phases each mode uses (bit MODE set → per-element index
+  // math, clear → XOR-composed addresses).  Measured on B200 (2^24, profiles/): the XOR-composed
+  // phases win for the strided pass 1 (0.287 → 0.267 ms); for the contiguous pass 2 the per-element
+  // form is faster (0.197 vs 0.214 ms).
+#ifndef RONK_LOAD_V0_MASK
+#define RONK_LOAD_V0_MASK 5
+#endif
+#ifndef RONK_STORE_V0_MASK
+#define RONK_STORE_V0_MASK 5
+#endif
+  if ((RONK_LOAD_V0_MASK >> MODE) & 1) ntt_load_phase_v0<F, MODE>(smem, A, tile, tid, NTHR);
+  else ntt_load_phase<F, MODE>(smem, A, tile, tid, NTHR);
   __syncthreads();
   if (use_tw) mbar_wait(bar, 0);
   u32 nst, wb, lcur;
@@ -534,7 +635,8 @@ __global__ void __launch_bounds__(NTHR, MINB) ntt_tile_kernel(const F f, const N
     ntt_round_dispatch<F, INV>(f, smem, tw, A, nst, wb, lcur, tid, NTHR);
     __syncthreads();
   }
-  ntt_store_phase<F, MODE, INV>(f, smem, A, tile, tid, NTHR);
+  if ((RONK_STORE_V0_MASK >> MODE) & 1) ntt_store_phase_v0<F, MODE, INV>(f, smem, A, tile, tid, NTHR);
+  else ntt_store_phase<F, MODE, INV>(f, smem, A, tile, tid, NTHR);
 }
 
 // tab[i] = to_tw(w^i · s) for i < count  (plan building; w, s plain residues)
