@@ -143,8 +143,8 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
   u32 tile1, tile2;
   ntt_pass_tiles(log_n, (u32)pref1, (u32)pref2, &tile1, &tile2);
   // pass 1: N1-point transforms down the columns, inter-pass twiddle, blocked write to the workspace
-  const NttTileArgs A1 = ntt_args_pass1(data, (u64*)ctx->ws, pl.tw1, pl.tw_lo, INV ? pl.tw_hi_inv : pl.tw2, log_n,
-                                        batch, tile1, tile2, &tiles);
+  const NttTileArgs A1 = ntt_args_pass1(data, (u64*)ctx->ws, pl.tw1, pl.tw_lo, INV ? pl.tw_hi_inv : pl.tw2, pl.tw2,
+                                        log_n, batch, tile1, tile2, &tiles);
   if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
   RONK_TRY((launch_tile<F, MODE_PASS1, INV>(ctx, f, A1, (u32)tiles, INV ? "intt_pass1" : "ntt_pass1")));
   // pass 2: N2-point transforms along the contiguous workspace tiles, natural-order output

@@ -39,6 +39,7 @@ struct NttTileArgs {
   const u64* tw_tile;  // ω_M^e, e ∈ [0, M), twiddle form (M = 2^log_m)
   const u64* tw_lo;    // PASS1: ω_n^x, x ∈ [0, 2^log_lo)
   const u64* tw_hi;    // PASS1: ω_n^(y·2^log_lo) (· n^-1 for the inverse), y ∈ [0, n >> log_lo)
+  const u64* tw_hi_plain;  // PASS1: the same table without the n^-1 factor (twiddle stepping ratio)
   const u64* mul_src;  // optional point-wise multiplier, indexed like dst
   u64 scale;           // SINGLE + inverse: n^-1 in twiddle form
   u64 total;           // SINGLE: number of valid elements (batch·n)
@@ -279,6 +280,29 @@ RONK_DEV void ntt_store_phase(const F& f, const u64* smem, const NttTileArgs& A,
     const u32 nmask = (A.log_n >= 32) ? 0xFFFFFFFFu : ((1u << A.log_n) - 1u);
     const u32 lomask = (1u << A.log_lo) - 1u;
     const u64 base = (u64)b << A.log_n;
+    if (kk >= cl) {
+      // (column, k1 % C2) are fixed per thread and k1 advances by a constant per iteration, so the
+      // inter-pass twiddle ω_n^(j2·k1) is STEPPED: w ← w·ρ with ρ = ω_n^(j2·Δk1) — one multiply
+      // instead of two table gathers, the index arithmetic and the combine-multiply.
+      const u32 rem = tid & ((1u << cl) - 1u);
+      const u32 c = rem >> lc2, k1_in = rem & ((1u << lc2) - 1u);
+      const u32 j2 = (sub << lc) | c;
+      const u32 k1_t = ((tid >> cl) << lc2) | k1_in;
+      const u32 dk1 = (1u << (kk - cl)) << lc2;
+      u32 ex0 = j2 * k1_t, exd = j2 * dk1;
+      if (INV) { ex0 = (0u - ex0) & nmask; exd = (0u - exd) & nmask; }
+      u64 w = f.mul_tw(ld_tw(A.tw_lo + (ex0 & lomask)), ld_tw(A.tw_hi + (ex0 >> A.log_lo)));
+      const u64 rho = f.mul_tw(ld_tw(A.tw_lo + (exd & lomask)), ld_tw(A.tw_hi_plain + (exd >> A.log_lo)));
+      const u64 dst_t = base + ((u64)(tid >> cl) << (A.log_n2 + lc2)) + ((u64)j2 << lc2) + k1_in;
+      const u64 ddst = (u64)(1u << (kk - cl)) << (A.log_n2 + lc2);
+#pragma unroll 4
+      for (u32 j = 0; j < per_thread; j++) {
+        const u32 gj = j << kk;
+        const u64 v = f.mul_tw(smem[sw_t ^ swz(store_perm<MODE>(A, gj))], w);
+        A.dst[dst_t + (u64)j * ddst] = v;
+        w = f.mul_tw(w, rho);
+      }
+    } else {
 #pragma unroll 4
     for (u32 j = 0; j < per_thread; j++) {
       const u32 gj = j << kk;
@@ -293,6 +317,7 @@ RONK_DEV void ntt_store_phase(const F& f, const u64* smem, const NttTileArgs& A,
       const u64 w = f.mul_tw(ld_tw(A.tw_lo + (ex & lomask)), ld_tw(A.tw_hi + (ex >> A.log_lo)));
       const u64 v = f.mul_tw(smem[sw_t ^ swz(store_perm<MODE>(A, gj))], w);
       A.dst[base + ((u64)k1_blk << (A.log_n2 + lc2)) + ((u64)j2 << lc2) + k1_in] = v;
+    }
     }
   } else {
     const u32 lc2 = A.log_c;  // pass-2 tile: columns are the C2 adjacent k1 values
@@ -447,7 +472,7 @@ inline void ntt_pass_tiles(u32 log_n, u32 pref1, u32 pref2, u32* t1, u32* t2) {
   *t2 = pref2 < sh.log_n2 ? sh.log_n2 : (pref2 > NTT_TILE_LOG_MAX ? NTT_TILE_LOG_MAX : pref2);
 }
 inline NttTileArgs ntt_args_pass1(const u64* data, u64* ws, const u64* tw1, const u64* tw_lo, const u64* tw_hi,
-                                  u32 log_n, u32 batch, u32 tile1, u32 tile2, u64* tiles) {
+                                  const u64* tw_hi_plain, u32 log_n, u32 batch, u32 tile1, u32 tile2, u64* tiles) {
   const NttShape sh = ntt_shape(log_n);
   NttTileArgs A = {};
   A.src = data;
@@ -455,6 +480,7 @@ inline NttTileArgs ntt_args_pass1(const u64* data, u64* ws, const u64* tw1, cons
   A.tw_tile = tw1;
   A.tw_lo = tw_lo;
   A.tw_hi = tw_hi;
+  A.tw_hi_plain = tw_hi_plain;
   A.tile_log = tile1;
   A.log_m = sh.log_n1;
   A.log_c = tile1 - sh.log_n1;

@@ -82,8 +82,8 @@ int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 l
   std::vector<u64> ws((size_t)batch << log_n);
   u32 tile1, tile2;
   ntt_pass_tiles(log_n, pref1, pref2, &tile1, &tile2);
-  NttTileArgs A1 = ntt_args_pass1(data, ws.data(), tw1.data(), tw_lo.data(), INV ? tw_hi_inv.data() : tw2.data(), log_n,
-                                  batch, tile1, tile2, &tiles);
+  NttTileArgs A1 = ntt_args_pass1(data, ws.data(), tw1.data(), tw_lo.data(), INV ? tw_hi_inv.data() : tw2.data(),
+                                  tw2.data(), log_n, batch, tile1, tile2, &tiles);
   run_tiles<F, MODE_PASS1, INV>(f, A1, tiles);
   NttTileArgs A2 = ntt_args_pass2(ws.data(), data, mul, tw2.data(), log_n, batch, tile2, &tiles);
   run_tiles<F, MODE_PASS2, INV>(f, A2, tiles);
