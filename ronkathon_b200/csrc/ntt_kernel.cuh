@@ -153,6 +153,9 @@ RONK_DEV void ntt_round(const F& f, u64* smem, const u64* tw, const NttTileArgs&
 #define RONK_LD_BATCH 8
 #endif
 constexpr int LD_BATCH = RONK_LD_BATCH;
+#ifndef RONK_LD_BATCH_CONTIG
+#define RONK_LD_BATCH_CONTIG 16
+#endif
 RONK_DEV u32 ilog2(u32 v) {
   u32 l = 0;
   while ((1u << l) < v) l++;
@@ -348,10 +351,11 @@ RONK_DEV void ntt_load_phase_v0(u64* smem, const NttTileArgs& A, u32 tile, u32 t
   else if (MODE == MODE_PASS1) base = ((u64)b << A.log_n) + ((u64)sub << A.log_c);
   else base = ((u64)b << A.log_n) + ((u64)sub << A.tile_log);
   const u32 cmask = (1u << A.log_c) - 1u;
-  for (u32 e0 = tid; e0 < T; e0 += nthr * LD_BATCH) {
-    u64 v[LD_BATCH];
+  constexpr int LB = (MODE == MODE_PASS1) ? LD_BATCH : RONK_LD_BATCH_CONTIG;
+  for (u32 e0 = tid; e0 < T; e0 += nthr * LB) {
+    u64 v[LB];
 #pragma unroll
-    for (int i = 0; i < LD_BATCH; i++) {
+    for (int i = 0; i < LB; i++) {
       const u32 e = e0 + i * nthr;
       if (MODE == MODE_SINGLE) {
         const u64 g = base + e;
@@ -364,7 +368,7 @@ RONK_DEV void ntt_load_phase_v0(u64* smem, const NttTileArgs& A, u32 tile, u32 t
       }
     }
 #pragma unroll
-    for (int i = 0; i < LD_BATCH; i++) {
+    for (int i = 0; i < LB; i++) {
       const u32 e = e0 + i * nthr;
       if (e < T) smem[swz(e)] = v[i];
     }
