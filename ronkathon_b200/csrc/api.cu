@@ -52,6 +52,10 @@ int ronk_ctx_destroy(ronk_ctx* ctx) {
     NttPlan& p = kv.second;
     if (p.tw1) cudaFree(p.tw1);
     if (p.tw2) cudaFree(p.tw2);
+    for (int d = 0; d < 2; d++) {
+      if (p.tw1_2d[d]) cudaFree(p.tw1_2d[d]);
+      if (p.tw2_2d[d]) cudaFree(p.tw2_2d[d]);
+    }
     if (p.tw_lo) cudaFree(p.tw_lo);
     if (p.tw_hi_inv) cudaFree(p.tw_hi_inv);
   }

@@ -41,6 +41,21 @@ static int build_table(ronk_ctx* ctx, const F& f, u64 w, u64 s, u64** tab, u32 c
   return check_launch(ctx, "pow_table_kernel");
 }
 
+static int build_tw2d(ronk_ctx* ctx, const u64* tw1d, u32 log_m, u64* out2d[2]) {
+  u32 off[4];
+  const u32 words = ntt_tw2d_layout(log_m, off);
+  for (int d = 0; d < 2; d++) {
+    RONK_CUDA(ctx, cudaMalloc((void**)&out2d[d], (size_t)(words ? words : 2) * sizeof(u64)));
+    if (!words) continue;
+    {
+      LaunchScope ls(ctx, "tw2d_gather");
+      tw2d_gather_kernel<<<(words + 255) / 256, 256, 0, ctx->stream>>>(tw1d, log_m, d, out2d[d], words);
+    }
+    RONK_TRY(check_launch(ctx, "tw2d_gather_kernel"));
+  }
+  return RONK_OK;
+}
+
 template <class F>
 static int build_plan(ronk_ctx* ctx, const F& f, u64 p, u64 g, u32 log_n, NttPlan* plan) {
   const u64 n = (u64)1 << log_n;
@@ -53,6 +68,7 @@ static int build_plan(ronk_ctx* ctx, const F& f, u64 p, u64 g, u32 log_n, NttPla
   if (!sh.two_pass) {
     plan->two_pass = false;
     RONK_TRY(build_table(ctx, f, w, 1, &plan->tw1, (u32)n));
+    RONK_TRY(build_tw2d(ctx, plan->tw1, log_n, plan->tw1_2d));
   } else {
     plan->two_pass = true;
     plan->log_n1 = sh.log_n1;
@@ -62,6 +78,8 @@ static int build_plan(ronk_ctx* ctx, const F& f, u64 p, u64 g, u32 log_n, NttPla
     RONK_TRY(build_table(ctx, f, h_powmod(w, n1, p), 1, &plan->tw2, (u32)n2));
     RONK_TRY(build_table(ctx, f, w, 1, &plan->tw_lo, (u32)n1));
     RONK_TRY(build_table(ctx, f, h_powmod(w, n1, p), ninv, &plan->tw_hi_inv, (u32)n2));
+    RONK_TRY(build_tw2d(ctx, plan->tw1, plan->log_n1, plan->tw1_2d));
+    RONK_TRY(build_tw2d(ctx, plan->tw2, plan->log_n2, plan->tw2_2d));
   }
   // n^-1 in twiddle form: Goldilocks → plain; Montgomery → ninv·R mod p
   if (p == GL_P && g == 7) plan->scale_inv = ninv;
@@ -71,7 +89,7 @@ static int build_plan(ronk_ctx* ctx, const F& f, u64 p, u64 g, u32 log_n, NttPla
 
 template <class F, int MODE, bool INV, int NTHR, int MINB>
 static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
-  const size_t smem = ((size_t)1 << A.tile_log) * sizeof(u64) + ((size_t)1 << A.log_m) * sizeof(u64) + 16;
+  const size_t smem = ((size_t)1 << A.tile_log) * sizeof(u64) + (size_t)A.tw_words * sizeof(u64) + 16;
   // set on every launch: the attribute is per device, and several contexts may live in one process
   RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_tile_kernel<F, MODE, INV, NTHR, MINB>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -84,7 +102,7 @@ static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 ti
 
 template <class F, int MODE, bool INV>
 static int launch_pipe(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
-  const size_t smem = ((size_t)2 << A.tile_log) * sizeof(u64) + ((size_t)1 << A.log_m) * sizeof(u64) + 16;
+  const size_t smem = ((size_t)2 << A.tile_log) * sizeof(u64) + (size_t)A.tw_words * sizeof(u64) + 16;
   RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_pipe_kernel<F, MODE, INV, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       226 * 1024));
   const u32 grid = tiles < (u32)ctx->sm_count ? tiles : (u32)ctx->sm_count;
@@ -111,7 +129,7 @@ static int launch_tile(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tile
   }
   // 2^13-element tiles with enough of them to keep every SM busy: persistent + cp.async double buffering
   if (pipe && A.tile_log == 13 && A.log_m <= 13 && tiles >= 2u * (u32)ctx->sm_count &&
-      ((size_t)2 << 13) * 8 + ((size_t)1 << A.log_m) * 8 + 16 <= 226 * 1024)
+      ((size_t)2 << 13) * 8 + (size_t)A.tw_words * 8 + 16 <= 226 * 1024)
     return launch_pipe<F, MODE, INV>(ctx, f, A, tiles, name);
   if (groups >= 1024) return launch_tile_n<F, MODE, INV, 512, 1>(ctx, f, A, tiles, name);
   if (groups >= 512) return launch_tile_n<F, MODE, INV, 256, 2>(ctx, f, A, tiles, name);
@@ -127,7 +145,7 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
     u32 cap = 12;
     if (const char* s = getenv("RONK_SINGLE_TILE_LOG")) cap = (u32)atoi(s);
     const NttTileArgs A =
-        ntt_args_single(data, mul, pl.tw1, pl.scale_inv, log_n, (u64)batch << log_n, INV, cap, &tiles);
+        ntt_args_single(data, mul, pl.tw1_2d[INV ? 1 : 0], pl.scale_inv, log_n, (u64)batch << log_n, INV, cap, &tiles);
     if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
     return launch_tile<F, MODE_SINGLE, INV>(ctx, f, A, (u32)tiles, INV ? "intt_single" : "ntt_single");
   }
@@ -143,12 +161,12 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
   u32 tile1, tile2;
   ntt_pass_tiles(log_n, (u32)pref1, (u32)pref2, &tile1, &tile2);
   // pass 1: N1-point transforms down the columns, inter-pass twiddle, blocked write to the workspace
-  const NttTileArgs A1 = ntt_args_pass1(data, (u64*)ctx->ws, pl.tw1, pl.tw_lo, INV ? pl.tw_hi_inv : pl.tw2, pl.tw2,
+  const NttTileArgs A1 = ntt_args_pass1(data, (u64*)ctx->ws, pl.tw1_2d[INV ? 1 : 0], pl.tw_lo, INV ? pl.tw_hi_inv : pl.tw2, pl.tw2,
                                         log_n, batch, tile1, tile2, &tiles);
   if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
   RONK_TRY((launch_tile<F, MODE_PASS1, INV>(ctx, f, A1, (u32)tiles, INV ? "intt_pass1" : "ntt_pass1")));
   // pass 2: N2-point transforms along the contiguous workspace tiles, natural-order output
-  const NttTileArgs A2 = ntt_args_pass2((const u64*)ctx->ws, data, mul, pl.tw2, log_n, batch, tile2, &tiles);
+  const NttTileArgs A2 = ntt_args_pass2((const u64*)ctx->ws, data, mul, pl.tw2_2d[INV ? 1 : 0], log_n, batch, tile2, &tiles);
   if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
   return launch_tile<F, MODE_PASS2, INV>(ctx, f, A2, (u32)tiles, INV ? "intt_pass2" : "ntt_pass2");
 }

@@ -36,7 +36,9 @@ enum { NTT_FLAG_SCALE = 1, NTT_FLAG_MUL = 2 };
 struct NttTileArgs {
   const u64* src;
   u64* dst;
-  const u64* tw_tile;  // ω_M^e, e ∈ [0, M), twiddle form (M = 2^log_m)
+  const u64* tw_tile;  // per-round 2-D twiddle tables (see ntt_tw2d_layout), twiddle form
+  u32 tw_off[4];       // start of round r's table inside tw_tile (in words)
+  u32 tw_words;        // total words of tw_tile (even)
   const u64* tw_lo;    // PASS1: ω_n^x, x ∈ [0, 2^log_lo)
   const u64* tw_hi;    // PASS1: ω_n^(y·2^log_lo) (· n^-1 for the inverse), y ∈ [0, n >> log_lo)
   const u64* tw_hi_plain;  // PASS1: the same table without the n^-1 factor (twiddle stepping ratio)
@@ -96,6 +98,39 @@ RONK_DEV void radix_network(const F& f, u64 (&x)[16]) {
   if constexpr (NST >= 1) bf_level<0, INV>(f, x, seq{});
 }
 
+// Per-round 2-D twiddle tables.  Round r works on sub-transforms of length L = 2^lcur
+// (lcur = log_m - 4r, only while lcur > 4) and needs ω_L^(i2·k1) for i2 < L/16, k1 < 16.
+// Layout: row i2 holds the 16 values k1 = 0..15 plus one pad word (row stride 17 words), so a thread
+// reads its 15 twiddles at fixed offsets from one base (LDS [R + imm], no index arithmetic) and the
+// lanes of a warp (consecutive i2) hit distinct banks.
+constexpr u32 TW_ROW = 17;
+RONK_HD u32 ntt_tw2d_layout(u32 log_m, u32 off[4]) {
+  u32 total = 0, r = 0;
+  for (u32 lcur = log_m; lcur > 4 && r < 4; lcur -= 4, r++) {
+    off[r] = total;
+    total += TW_ROW << (lcur - 4);
+  }
+  for (; r < 4; r++) off[r] = total;
+  return (total + 1u) & ~1u;  // even number of words: the TMA bulk copy moves multiples of 16 bytes
+}
+// word w of the 2-D table → index into the 1-D table ω_M^e (or its negation for the inverse)
+RONK_HD u32 ntt_tw2d_source(u32 log_m, u32 w, bool inverse, bool* valid) {
+  u32 off[4];
+  const u32 total = ntt_tw2d_layout(log_m, off);
+  *valid = false;
+  if (w >= total) return 0;
+  u32 r = 0, lcur = log_m;
+  while (r < 3 && lcur - 4 > 4 && w >= off[r + 1]) { r++; lcur -= 4; }
+  const u32 rel = w - off[r];
+  const u32 i2 = rel / TW_ROW, k1 = rel % TW_ROW;
+  if (lcur <= 4 || i2 >= (1u << (lcur - 4)) || k1 >= 16) return 0;  // pad words
+  *valid = true;
+  const u32 M1 = (1u << log_m) - 1u;
+  u32 idx = ((i2 * k1) << (log_m - lcur)) & M1;
+  if (inverse) idx = (0u - idx) & M1;
+  return idx;
+}
+
 // One round: gather the window [wb, wb+4) of the tile index into registers, butterfly, twiddle,
 // scatter back in place.  `lcur` = log2 of the current sub-transform length (only used when NST==4).
 template <int NST, bool INV, class F>
@@ -121,15 +156,12 @@ RONK_DEV void ntt_round(const F& f, u64* smem, const u64* tw, const NttTileArgs&
   }
   radix_network<NST, INV>(f, x);
   if (NST == 4 && lcur > 4) {
-    const u32 M1 = (1u << A.log_m) - 1u;
     const u32 i2 = (e0 >> A.log_c) & ((1u << (lcur - 4)) - 1u);
-    const u32 step = i2 << (A.log_m - lcur);
+    const u64* row = tw + A.tw_off[(A.log_m - lcur) >> 2] + i2 * TW_ROW;  // this round's table, row i2
 #pragma unroll
     for (int j = 1; j < 16; j++) {
-      const u32 k1 = ((j & 1) << 3) | ((j & 2) << 1) | ((j & 4) >> 1) | ((j & 8) >> 3);
-      u32 idx = (step * k1) & M1;
-      if (INV) idx = (0u - idx) & M1;
-      x[j] = f.mul_tw(x[j], tw[idx]);
+      const int k1 = ((j & 1) << 3) | ((j & 2) << 1) | ((j & 4) >> 1) | ((j & 8) >> 3);
+      x[j] = f.mul_tw(x[j], row[k1]);
     }
   }
   {
@@ -457,6 +489,7 @@ inline NttTileArgs ntt_args_single(u64* data, const u64* mul, const u64* tw, u64
   A.src = data;
   A.dst = data;
   A.tw_tile = tw;
+  A.tw_words = ntt_tw2d_layout(log_n, A.tw_off);
   A.mul_src = mul;
   A.scale = scale_inv;
   A.total = total;
@@ -482,6 +515,7 @@ inline NttTileArgs ntt_args_pass1(const u64* data, u64* ws, const u64* tw1, cons
   A.src = data;
   A.dst = ws;
   A.tw_tile = tw1;
+  A.tw_words = ntt_tw2d_layout(sh.log_n1, A.tw_off);
   A.tw_lo = tw_lo;
   A.tw_hi = tw_hi;
   A.tw_hi_plain = tw_hi_plain;
@@ -504,6 +538,7 @@ inline NttTileArgs ntt_args_pass2(const u64* ws, u64* data, const u64* mul, cons
   A.src = ws;
   A.dst = data;
   A.tw_tile = tw2;
+  A.tw_words = ntt_tw2d_layout(sh.log_n2, A.tw_off);
   A.mul_src = mul;
   A.tile_log = tile2;
   A.log_m = sh.log_n2;
@@ -600,15 +635,15 @@ __global__ void __launch_bounds__(NTHR, 1) ntt_pipe_kernel(const F f, const NttT
   u64* buf0 = smem;
   u64* buf1 = smem + T;
   u64* tw = smem + 2 * T;
-  u64* bar = tw + M;
+  u64* bar = tw + A.tw_words;
   const bool use_tw = A.log_m > 4;
   u32 t = blockIdx.x;
   if (t >= tiles) return;
   if (use_tw && tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar, M * 8u);
-    tma_bulk_g2s(tw, A.tw_tile, M * 8u, bar);
+    mbar_expect_tx(bar, A.tw_words * 8u);
+    tma_bulk_g2s(tw, A.tw_tile, A.tw_words * 8u, bar);
   }
   ntt_load_async<F, MODE>(buf0, A, t, tid, NTHR);
   cp_async_commit();
@@ -638,13 +673,13 @@ __global__ void __launch_bounds__(NTHR, MINB) ntt_tile_kernel(const F f, const N
   const u32 tid = threadIdx.x, tile = blockIdx.x;
   const u32 T = 1u << A.tile_log, M = 1u << A.log_m;
   u64* tw = smem + T;
-  u64* bar = tw + M;
+  u64* bar = tw + A.tw_words;
   const bool use_tw = A.log_m > 4;  // a single radix-16 round has no general twiddles
   if (use_tw && tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar, M * 8u);
-    tma_bulk_g2s(tw, A.tw_tile, M * 8u, bar);  // lands while the tile itself is being loaded
+    mbar_expect_tx(bar, A.tw_words * 8u);
+    tma_bulk_g2s(tw, A.tw_tile, A.tw_words * 8u, bar);  // lands while the tile itself is being loaded
   }
   // Which formulation of the load/store phases each mode uses (bit MODE set → per-element index
   // math, clear → XOR-composed addresses).  Measured on B200 (2^24, profiles/): the XOR-composed
@@ -667,6 +702,15 @@ __global__ void __launch_bounds__(NTHR, MINB) ntt_tile_kernel(const F f, const N
   }
   if ((RONK_STORE_V0_MASK >> MODE) & 1) ntt_store_phase_v0<F, MODE, INV>(f, smem, A, tile, tid, NTHR);
   else ntt_store_phase<F, MODE, INV>(f, smem, A, tile, tid, NTHR);
+}
+
+// 2-D per-round twiddle table from the 1-D table ω_M^e (both in twiddle form); pads = 0
+static __global__ void tw2d_gather_kernel(const u64* __restrict__ tw1d, u32 log_m, int inverse, u64* __restrict__ out, u32 words) {
+  const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= words) return;
+  bool valid;
+  const u32 idx = ntt_tw2d_source(log_m, w, inverse != 0, &valid);
+  out[w] = valid ? tw1d[idx] : 0ULL;
 }
 
 // tab[i] = to_tw(w^i · s) for i < count  (plan building; w, s plain residues)

@@ -27,6 +27,8 @@ struct NttPlan {
   u32 log_n1 = 0, log_n2 = 0;
   u64* tw1 = nullptr;        // ω_{N1}^e (single pass: ω_n^e), twiddle form
   u64* tw2 = nullptr;        // ω_{N2}^e == ω_n^(e·N1)
+  u64* tw1_2d[2] = {nullptr, nullptr};  // per-round 2-D tables of pass 1 / single (forward, inverse)
+  u64* tw2_2d[2] = {nullptr, nullptr};  // per-round 2-D tables of pass 2
   u64* tw_lo = nullptr;      // ω_n^x, x < N1
   u64* tw_hi_inv = nullptr;  // ω_n^(y·N1) · n^-1
   u64 scale_inv = 0;         // n^-1, twiddle form (single-pass inverse)

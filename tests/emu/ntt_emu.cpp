@@ -46,6 +46,19 @@ std::vector<u64> table(const F& f, u64 w, u64 s, u64 count) {  // pow_table_kern
   return t;
 }
 
+// mirrors tw2d_gather_kernel
+std::vector<u64> table2d(const std::vector<u64>& tw1d, u32 log_m, bool inverse) {
+  u32 off[4];
+  const u32 words = ntt_tw2d_layout(log_m, off);
+  std::vector<u64> out(words ? words : 2, 0);
+  for (u32 w = 0; w < words; w++) {
+    bool valid;
+    const u32 idx = ntt_tw2d_source(log_m, w, inverse, &valid);
+    out[w] = valid ? tw1d[idx] : 0;
+  }
+  return out;
+}
+
 template <class F, int MODE, bool INV>
 void run_tiles(const F& f, const NttTileArgs& A, u64 tiles) {
   const u32 T = 1u << A.tile_log, nthr = (T / 32 >= 32) ? T / 32 : 32;
@@ -69,7 +82,8 @@ int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 l
   const NttShape sh = ntt_shape(log_n);
   u64 tiles = 0;
   if (!sh.two_pass) {
-    auto tw = table(f, w, 1, n);
+    auto tw1d = table(f, w, 1, n);
+    auto tw = table2d(tw1d, log_n, INV);
     NttTileArgs A = ntt_args_single(data, mul, tw.data(), scale, log_n, (u64)batch << log_n, INV, tile_cap, &tiles);
     run_tiles<F, MODE_SINGLE, INV>(f, A, tiles);
     return 0;
@@ -82,10 +96,12 @@ int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 l
   std::vector<u64> ws((size_t)batch << log_n);
   u32 tile1, tile2;
   ntt_pass_tiles(log_n, pref1, pref2, &tile1, &tile2);
-  NttTileArgs A1 = ntt_args_pass1(data, ws.data(), tw1.data(), tw_lo.data(), INV ? tw_hi_inv.data() : tw2.data(),
+  auto tw1_2d = table2d(tw1, sh.log_n1, INV);
+  auto tw2_2d = table2d(tw2, sh.log_n2, INV);
+  NttTileArgs A1 = ntt_args_pass1(data, ws.data(), tw1_2d.data(), tw_lo.data(), INV ? tw_hi_inv.data() : tw2.data(),
                                   tw2.data(), log_n, batch, tile1, tile2, &tiles);
   run_tiles<F, MODE_PASS1, INV>(f, A1, tiles);
-  NttTileArgs A2 = ntt_args_pass2(ws.data(), data, mul, tw2.data(), log_n, batch, tile2, &tiles);
+  NttTileArgs A2 = ntt_args_pass2(ws.data(), data, mul, tw2_2d.data(), log_n, batch, tile2, &tiles);
   run_tiles<F, MODE_PASS2, INV>(f, A2, tiles);
   return 0;
 }
