@@ -631,7 +631,7 @@ template <class F, int MODE, bool INV, int NTHR>
 __global__ void __launch_bounds__(NTHR, 1) ntt_pipe_kernel(const F f, const NttTileArgs A, const u32 tiles) {
   extern __shared__ __align__(128) u64 smem[];
   const u32 tid = threadIdx.x;
-  const u32 T = 1u << A.tile_log, M = 1u << A.log_m;
+  const u32 T = 1u << A.tile_log;
   u64* buf0 = smem;
   u64* buf1 = smem + T;
   u64* tw = smem + 2 * T;
@@ -671,7 +671,7 @@ template <class F, int MODE, bool INV, int NTHR, int MINB>
 __global__ void __launch_bounds__(NTHR, MINB) ntt_tile_kernel(const F f, const NttTileArgs A) {
   extern __shared__ __align__(128) u64 smem[];
   const u32 tid = threadIdx.x, tile = blockIdx.x;
-  const u32 T = 1u << A.tile_log, M = 1u << A.log_m;
+  const u32 T = 1u << A.tile_log;
   u64* tw = smem + T;
   u64* bar = tw + A.tw_words;
   const bool use_tw = A.log_m > 4;  // a single radix-16 round has no general twiddles

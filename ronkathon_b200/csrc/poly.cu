@@ -146,6 +146,158 @@ __global__ void poly_divrem_kernel(const F f, const u64* a, u32 da, const u64* b
   }
 }
 
+
+// ---- division by a linear factor (b0 + b1·x), §8f row 1 ------------------------------------------
+// quotient_and_remainder (mod.rs:170-225) specialised to the divisor kzg::open builds
+// (kzg/setup.rs:72-75: [-z, 1]).  With z = -b0/b1 the long division is the suffix recurrence
+//   h_j = a_j + z·h_{j+1}  (h_d = 0),   q_j = h_{j+1} / b1,   r = h_0 = a(z),
+// a first-order linear recurrence, i.e. a scan: (1) every chunk of 4096 coefficients is folded to
+// its Horner value S_c = Σ a_{c0+i} z^i, (2) one CTA turns the S_c into the carry-in of every chunk,
+// (3) every chunk redoes its local scan seeded with the carry and writes q.  2 reads + 1 write per
+// coefficient; the general single-CTA kernel above needs O(D) sequential steps for the same result.
+constexpr int DL_THR = 256, DL_PER = 16, DL_CHUNK = DL_THR * DL_PER;
+RONK_DEV u32 dl_pad(u32 i) { return i + (i >> 4); }  // 16-word rows padded to 17: conflict-free both ways
+
+template <class F>
+RONK_DEV u64 pow2k_tw(const F& f, u64 x_tw, int k) {  // x^(2^k), twiddle form in and out
+  for (int i = 0; i < k; i++) x_tw = f.mul_tw(x_tw, x_tw);
+  return x_tw;
+}
+
+template <class F, bool APPLY>
+__global__ void __launch_bounds__(DL_THR)
+div_linear_kernel(const F f, const u64* __restrict__ a, u64 d, u64 z, const u64* __restrict__ carry, u64* __restrict__ S,
+                  u64 scale, u64* __restrict__ q, u64* __restrict__ rem) {
+  __shared__ u64 tile[DL_CHUNK + DL_CHUNK / 16];
+  __shared__ u64 v[DL_THR + 1];
+  const u32 tid = threadIdx.x;
+  const u64 c0 = (u64)blockIdx.x * DL_CHUNK;
+  const u64 z_tw = f.to_tw(z);
+  for (u32 i = tid; i < (u32)DL_CHUNK; i += DL_THR) tile[dl_pad(i)] = (c0 + i < d) ? a[c0 + i] : 0ULL;  // coalesced
+  __syncthreads();
+  u64 x[DL_PER];
+#pragma unroll
+  for (int k = 0; k < DL_PER; k++) x[k] = tile[dl_pad(tid * DL_PER + k)];
+  u64 t = 0;  // Σ_k x[k] z^k
+#pragma unroll
+  for (int k = DL_PER - 1; k >= 0; k--) t = f.add(x[k], f.mul_tw(t, z_tw));
+  v[tid] = t;
+  if (tid == 0) v[DL_THR] = APPLY ? carry[blockIdx.x] : 0ULL;  // element 256 = carry into this chunk
+  u64 M = pow2k_tw(f, z_tw, 4);                                  // z^16
+  for (u32 off = 1; off <= (u32)DL_THR; off <<= 1) {             // suffix scan, uniform multiplier per level
+    __syncthreads();
+    const bool on = tid + off <= (u32)DL_THR;
+    const u64 other = on ? v[tid + off] : 0ULL;
+    __syncthreads();
+    if (on) v[tid] = f.add(v[tid], f.mul_tw(other, M));
+    M = f.mul_tw(M, M);
+  }
+  __syncthreads();
+  if (!APPLY) {
+    if (tid == 0) S[blockIdx.x] = v[0];
+    return;
+  }
+  const u64 s_tw = f.to_tw(scale);
+  u64 run = v[tid + 1];  // h at the first index above this thread's range
+#pragma unroll
+  for (int k = DL_PER - 1; k >= 0; k--) {
+    run = f.add(x[k], f.mul_tw(run, z_tw));  // h_{base+k}
+    x[k] = run;
+  }
+  if (blockIdx.x == 0 && tid == 0) rem[0] = x[0];  // r = h_0 (not scaled: a = q·(b1·x + b0) + r)
+#pragma unroll
+  for (int k = 0; k < DL_PER; k++) tile[dl_pad(tid * DL_PER + k)] = f.mul_tw(x[k], s_tw);
+  __syncthreads();
+  // q_j = h_{j+1}/b1: h at chunk position i goes to q[c0 + i - 1]; the top coefficient q_{d-1} is 0
+  for (u32 i = tid; i < (u32)DL_CHUNK; i += DL_THR) {
+    const u64 j = c0 + i;
+    if (j >= 1 && j < d) q[j - 1] = tile[dl_pad(i)];
+  }
+  if (c0 + DL_CHUNK >= d && c0 < d && tid == 0) q[d - 1] = 0ULL;
+}
+
+// carry[c] = Σ_{c' > c} S_{c'} Z^{c'-c-1}, Z = z^4096.  One CTA: every thread owns a contiguous block of
+// chunks (local Horner), thread 0 chains the ≤ 1024 block values, then every thread replays its block.
+template <class F>
+__global__ void __launch_bounds__(1024)
+div_linear_carry_kernel(const F f, const u64* __restrict__ S, u32 nchunks, u64 z, u64* __restrict__ carry) {
+  __shared__ u64 L[1024];
+  __shared__ u64 G[1025];
+  const u32 t = threadIdx.x;
+  const u64 Z = pow2k_tw(f, f.to_tw(z), 12);
+  const u32 B = (nchunks + 1023) / 1024;
+  const u32 lo = (u32)min((u64)t * B, (u64)nchunks), hi = (u32)min((u64)lo + B, (u64)nchunks);
+  u64 acc = 0;
+  for (u32 c = hi; c-- > lo;) acc = f.add(S[c], f.mul_tw(acc, Z));
+  L[t] = acc;
+  __syncthreads();
+  if (t == 0) {
+    u64 ZB = f.to_tw(1 % f.modulus());  // Z^B
+    {
+      u64 base = Z;
+      for (u32 e = B; e; e >>= 1) {
+        if (e & 1) ZB = f.mul_tw(ZB, base);
+        base = f.mul_tw(base, base);
+      }
+    }
+    u64 g = 0;
+    G[1024] = 0;
+    for (u32 i = 1024; i-- > 0;) {
+      g = f.add(L[i], f.mul_tw(g, ZB));
+      G[i] = g;  // Horner value of all chunks from block i upwards
+    }
+  }
+  __syncthreads();
+  u64 run = G[t + 1];
+  for (u32 c = hi; c-- > lo;) {
+    carry[c] = run;
+    run = f.add(S[c], f.mul_tw(run, Z));
+  }
+}
+
+template <class F>
+static int div_linear_with_field(ronk_ctx* ctx, const F& f, const u64* a, size_t d, u64 z, u64 scale, u64* q, u64* rem) {
+  const size_t nchunks = (d + DL_CHUNK - 1) / DL_CHUNK;
+  if (nchunks > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "polynomial too long");
+  RONK_TRY(ensure_ws(ctx, &ctx->ws2, &ctx->ws2_bytes, 2 * nchunks * sizeof(u64)));
+  u64* S = (u64*)ctx->ws2;
+  u64* carry = S + nchunks;
+  {
+    LaunchScope ls(ctx, "div_linear_fold");
+    div_linear_kernel<F, false><<<(u32)nchunks, DL_THR, 0, ctx->stream>>>(f, a, d, z, nullptr, S, scale, nullptr, nullptr);
+  }
+  RONK_TRY(check_launch(ctx, "div_linear_kernel<fold>"));
+  {
+    LaunchScope ls(ctx, "div_linear_carry");
+    div_linear_carry_kernel<F><<<1, 1024, 0, ctx->stream>>>(f, S, (u32)nchunks, z, carry);
+  }
+  RONK_TRY(check_launch(ctx, "div_linear_carry_kernel"));
+  {
+    LaunchScope ls(ctx, "div_linear_apply");
+    div_linear_kernel<F, true><<<(u32)nchunks, DL_THR, 0, ctx->stream>>>(f, a, d, z, carry, nullptr, scale, q, rem);
+  }
+  return check_launch(ctx, "div_linear_kernel<apply>");
+}
+
+// a / (b0 + b1·x): q (d terms, top one 0) and the scalar remainder, all device pointers; q may not alias a.
+static int div_linear_device(ronk_ctx* ctx, u64 p, const u64* a, size_t d, u64 b0, u64 b1, u64* q, u64* rem) {
+  if (!ctx || !a || !q || !rem) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (q == a) return set_err(ctx, RONK_EINVAL, "the quotient may not alias the dividend");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (d == 0) return set_err(ctx, RONK_EINVAL, "empty dividend");
+  if (b0 >= p || b1 >= p) return set_err(ctx, RONK_EINVAL, "non-canonical divisor coefficient");
+  if (b1 == 0) return set_err(ctx, RONK_EINVAL, "divisor is not linear (leading coefficient 0)");
+  const u64 b1inv = h_powmod(b1, p - 2, p);
+  const u64 z = h_mulmod(b0 ? p - b0 : 0, b1inv, p);
+  if (p == GL_P) {
+    GoldilocksField f;
+    return div_linear_with_field(ctx, f, a, d, z, b1inv, q, rem);
+  }
+  MontField f;
+  RONK_TRY(make_mont_field(ctx, p, 0, false, &f));
+  return div_linear_with_field(ctx, f, a, d, z, b1inv, q, rem);
+}
+
 __global__ void pad_copy_kernel(u64* dst, const u64* src, size_t len, size_t n) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (i < len) ? src[i] : 0ULL;
@@ -308,6 +460,11 @@ int ronk_dft_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t* in, uint
   return dft_device(ctx, p, g, (const u64*)in, n, (u64*)out);
 }
 
+int ronk_poly_div_linear_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, size_t d, uint64_t b0, uint64_t b1,
+                             uint64_t* q, uint64_t* rem) {
+  return div_linear_device(ctx, p, (const u64*)a, d, b0, b1, (u64*)q, (u64*)rem);
+}
+
 // ---- host-pointer variants ---------------------------------------------------------------------
 static int up(ronk_ctx* ctx, u64** d, const void* h, size_t n) {
   RONK_CUDA(ctx, cudaMalloc((void**)d, (n ? n : 1) * sizeof(u64)));
@@ -392,9 +549,17 @@ int ronk_poly_divrem_u64_host(ronk_ctx* ctx, uint64_t p, const uint64_t* a, size
   if (da == 0) return RONK_OK;
   DevBuf A, B, Qd, Rd;
   RONK_TRY(up(ctx, &A.p, a, da));
-  RONK_TRY(up(ctx, &B.p, b, db));
   RONK_CUDA(ctx, cudaMalloc((void**)&Qd.p, da * sizeof(u64)));
   RONK_CUDA(ctx, cudaMalloc((void**)&Rd.p, da * sizeof(u64)));
+  if (db == 2 && b[1] != 0 && b[1] < p && b[0] < p) {
+    // linear divisor (the kzg::open case): device-wide scan instead of D sequential steps; the
+    // remainder is the constant a(z), zero-padded to da terms like the reference's array
+    RONK_CUDA(ctx, cudaMemsetAsync(Rd.p, 0, da * sizeof(u64), ctx->stream));
+    RONK_TRY(div_linear_device(ctx, p, A.p, da, b[0], b[1], Qd.p, Rd.p));
+    RONK_CUDA(ctx, cudaMemcpyAsync(q, Qd.p, da * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    return down(ctx, r, Rd.p, da);
+  }
+  RONK_TRY(up(ctx, &B.p, b, db));
   RONK_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
   if (p == GL_P) {
     GoldilocksField f;

@@ -73,6 +73,73 @@ def test_divrem_random_and_panics():
     assert np.array_equal(q.coefficients, eq) and np.array_equal(r.coefficients, er)
 
 
+def test_div_by_linear_factor_scan_vs_oracle_and_identity():
+    """§8f row 1: Polynomial::div/rem by the divisor kzg::open builds (kzg/setup.rs:72-75) runs as a
+    device-wide scan.  Bit-exact vs the literal long division of the oracle (mod.rs:170-225) at sizes
+    it finishes, and a = q·(b0 + b1·x) + r coefficient by coefficient at 2^22."""
+    from ronkathon_b200 import GoldilocksField, PlutoBaseField, PlutoScalarField, Polynomial
+    c = ctx()
+    rng = np.random.default_rng(11)
+    for F, p in ((PlutoBaseField, 101), (PlutoScalarField, 17), (GoldilocksField, GL)):
+        for d in (1, 2, 3, 15, 16, 17, 255, 4095, 4096, 4097, 8193, 9001):
+            a = oracle.splitmix(p, 100 + d, d)
+            for b in ([int(rng.integers(0, p, dtype=np.uint64)), 1],
+                      [int(rng.integers(0, p, dtype=np.uint64)), int(rng.integers(1, p, dtype=np.uint64))], [0, 1]):
+                q, r = Polynomial(a, F).quotient_and_remainder(Polynomial(b, F))
+                eq, er = oracle.poly_divrem(p, a, b)
+                assert np.array_equal(q.coefficients, eq) and np.array_equal(r.coefficients, er), (p, d, b)
+    # all-zero dividend, and a dividend the divisor divides exactly (remainder 0)
+    z = Polynomial([0] * 5000, GoldilocksField).quotient_and_remainder(Polynomial([5, 7], GoldilocksField))
+    assert not z[0].coefficients.any() and not z[1].coefficients.any()
+    base = oracle.splitmix(GL, 9, 4999)
+    exact = oracle.poly_mul(GL, base, [GL - 3, 1])                      # base·(x - 3), 5000 terms
+    q, r = Polynomial(exact, GoldilocksField).quotient_and_remainder(Polynomial([GL - 3, 1], GoldilocksField))
+    assert np.array_equal(q.coefficients[:-1], base) and q.coefficients[-1] == 0 and not r.coefficients.any()
+    # device-pointer entry at 2^22 (1024 chunks): identity check, remainder = a(z) by the evaluate kernel
+    d = 1 << 22
+    a = oracle.splitmix(GL, 77, d)
+    b0, b1 = 1234567890123456789 % GL, 987654321987654321 % GL
+    A, Q, R = dev(a), dev(np.zeros(d, np.uint64)), dev(np.zeros(1, np.uint64))
+    c.call("ronk_poly_div_linear_u64", GL, A.data_ptr(), d, b0, b1, Q.data_ptr(), R.data_ptr())
+    q, r = host(Q), host(R)
+    assert q[-1] == 0
+    recomposed = oracle.poly_add(GL, oracle.vec_mul(GL, q, np.full(d, b0, np.uint64)),
+                                 np.concatenate([np.zeros(1, np.uint64), oracle.vec_mul(GL, q, np.full(d, b1, np.uint64))[:-1]]))
+    recomposed[0] = oracle.add(GL, int(recomposed[0]), int(r[0]))
+    assert np.array_equal(recomposed, a)
+    zpt = oracle.mul(GL, GL - b0, oracle.inverse(GL, b1))
+    assert int(r[0]) == oracle.poly_eval_horner(GL, a, zpt)
+    with pytest.raises(Exception):
+        c.call("ronk_poly_div_linear_u64", GL, A.data_ptr(), d, b0, 0, Q.data_ptr(), R.data_ptr())
+    with pytest.raises(Exception):
+        c.call("ronk_poly_div_linear_u64", GL, A.data_ptr(), d, b0, b1, A.data_ptr(), R.data_ptr())
+
+
+def test_kzg_open_at_scale_matches_fast_oracle():
+    """commit→open on the device at a size the reference's const-generic arrays cannot reach:
+    2^16 F17 coefficients, quotient by the scan kernel, commitment by the bucket MSM."""
+    from ronkathon_b200 import kzg
+    from ronkathon_b200.curve import AffinePoint
+    from gpu_util import msm_inputs
+    ctx()
+    n = 1 << 16
+    pts, _ = msm_inputs(n)
+    coeffs = oracle.splitmix(17, 5, n)
+    zz = 4
+    out = kzg.open_([int(v) for v in coeffs], zz, pts)
+    q, _ = _synthetic(17, coeffs, zz)
+    assert out.raw == oracle.commit(q, pts, fast=True)
+
+
+def _synthetic(p, a, z):
+    """h_j = a_j + z·h_{j+1}; q_{j-1} = h_j, remainder h_0 (python ints)."""
+    hh, out = 0, [0] * len(a)
+    for j in range(len(a) - 1, 0, -1):
+        hh = (int(a[j]) + z * hh) % p
+        out[j - 1] = hh
+    return out, (int(a[0]) + z * hh) % p
+
+
 def test_poly_mul_paths_vs_oracle(gold64):
     from ronkathon_b200 import ops
     c = ctx()
