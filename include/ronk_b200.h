@@ -160,6 +160,11 @@ int ronk_poly_divrem_u64_host(ronk_ctx *ctx, uint64_t p, const uint64_t *a, size
  * device-wide scan.  Device pointers: a (d terms), q (d terms, q[d-1] = 0 like the reference's
  * zero-padded quotient), rem (1 word = a(-b0/b1)).  q must not alias a.  RONK_EINVAL for b1 == 0.
  * ronk_poly_divrem_u64_host takes this path by itself when db == 2 and b[1] != 0. */
+/* Lagrange interpolation through (xs[i], ys[i]), i < k: the monomial coefficients out[0..k).  This is
+ * Message::decode of src/codes/reed_solomon.rs:55-107 applied to the first K coordinates of a
+ * codeword (the reference enumerates combinations; the interpolant is unique).  Host pointers,
+ * k <= 8192.  RONK_EINVAL for a repeated x (the reference's `/` panics on the zero denominator). */
+int ronk_poly_interpolate_u64_host(ronk_ctx *ctx, uint64_t p, const uint64_t *xs, const uint64_t *ys, size_t k, uint64_t *out);
 int ronk_poly_div_linear_u64(ronk_ctx *ctx, uint64_t p, const uint64_t *a, size_t d, uint64_t b0, uint64_t b1, uint64_t *q, uint64_t *rem);
 
 /* ---- curve + kzg::commit ------------------------------------------------------------------ */

@@ -67,6 +67,7 @@ def lib():
             "orc_commit_fast": (i32, [pu8, u64, pu8, u64, pu8]),
             "orc_setup": (i32, [pu8, pu8]), "orc_open": (i32, [pu8, u64, C.c_uint8, pu8, u64, pu8]),
             "orc_rs_encode": (i32, [u64, u64, p64, u64, u64, p64, p64]),
+            "orc_rs_decode": (i32, [u64, p64, p64, u64, p64]),
             "orc_bench_fft_threads": (C.c_double, [u64, u64, u64, i32, p64]),
         }
         for name, (res, args) in sig.items():
@@ -221,6 +222,13 @@ def rs_encode(p, msg, n, g=None):
     msg = _arr(msg); xs, ys = np.empty(n, np.uint64), np.empty(n, np.uint64)
     _chk(lib().orc_rs_encode(p, generator(p) if g is None else g, _p64(msg), len(msg), n, _p64(xs), _p64(ys)))
     return xs, ys
+
+
+def rs_decode(p, xs, ys, k):
+    """Message::decode (codes/reed_solomon.rs:55-107) on the first k coordinates."""
+    xs, ys = _arr(xs)[:k].copy(), _arr(ys)[:k].copy(); out = np.empty(k, np.uint64)
+    _chk(lib().orc_rs_decode(p, _p64(xs), _p64(ys), k, _p64(out)))
+    return out
 
 
 # ---- GF(101^2), curve, kzg --------------------------------------------------------------------

@@ -598,6 +598,40 @@ int orc_rs_encode(u64 p, u64 g, const u64 *msg, u64 k, u64 n, u64 *xs, u64 *ys) 
   return ORC_OK;
 }
 
+/* Reed–Solomon decode (next row) — codes/reed_solomon.rs:55-107, literally: the first K coordinates
+ * are interpolated coefficient by coefficient,
+ *   data[i] = Σ_j  sign(i) · e_{K-1-i}(x without x_j) · y_j / Π_{k≠j} (x_k - x_j),
+ * sign(i) = -1 for odd i (:78-82), e_m = sum over all m-element combinations of the product (:83-89;
+ * the empty combination contributes ONE).  Exponential in K like the reference; K <= 20 here.
+ * A repeated x makes the denominator zero and `/` panics (prime/arithmetic.rs:54) -> ORC_EINVAL. */
+int orc_rs_decode(u64 p, const u64 *xs, const u64 *ys, u64 k, u64 *data) {
+  if (k > 20) return ORC_EINVAL;
+  for (u64 i = 0; i < k; i++) data[i] = 0;
+  for (u64 i = 0; i < k; i++) {
+    for (u64 j = 0; j < k; j++) {
+      u64 others[20];
+      u64 m = 0;
+      for (u64 t = 0; t < k; t++) if (t != j) others[m++] = xs[t];
+      const u64 want = k - 1 - i;
+      u64 esum = 0;
+      for (u64 mask = 0; mask < ((u64)1 << m); mask++) {
+        if ((u64)__builtin_popcountll(mask) != want) continue;
+        u64 prod = 1 % p;
+        for (u64 t = 0; t < m; t++) if (mask >> t & 1) prod = orc_mul(p, prod, others[t]);
+        esum = orc_add(p, esum, prod);
+      }
+      const u64 sign = (i % 2 == 1) ? orc_sub(p, 0, 1 % p) : 1 % p; /* :78-82 */
+      const u64 num = orc_mul(p, orc_mul(p, sign, esum), ys[j]);     /* :90-91 */
+      u64 den = 1 % p;                                               /* :94-100 */
+      for (u64 t = 0; t < k; t++) if (t != j) den = orc_mul(p, den, orc_sub(p, xs[t], xs[j]));
+      u64 dinv;
+      if (orc_inverse(p, den, &dinv)) return ORC_EINVAL;
+      data[i] = orc_add(p, data[i], orc_mul(p, num, dinv));          /* :102 */
+    }
+  }
+  return ORC_OK;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Timed CPU baseline entry points (bench.py cpu_baseline / --impl reference).
  * orc_bench_fft_threads: `threads` independent faithful fft_recursive transforms, one per thread

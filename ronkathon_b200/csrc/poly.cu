@@ -298,6 +298,101 @@ static int div_linear_device(ronk_ctx* ctx, u64 p, const u64* a, size_t d, u64 b
   return div_linear_with_field(ctx, f, a, d, z, b1inv, q, rem);
 }
 
+// ---- Lagrange interpolation (Reed–Solomon decode, §8f row 2) ------------------------------------
+// Message::decode (codes/reed_solomon.rs:55-107) interpolates the first K coordinates:
+//   data[i] = Σ_j y_j · (-1)^i e_{K-1-i}(x \ x_j) / Π_{k≠j}(x_k - x_j)
+// which is coefficient i of Σ_j y_j · M(X)/(X - x_j) / M'(x_j), M = Π (X - x_k).  The reference
+// enumerates combinations (exponential in K); the value is the unique interpolant, computed here as
+// (1) M by K in-place products, (2) per node j a synthetic division M/(X - x_j) giving q_j and
+// d_j = q_j(x_j) = Π_{k≠j}(x_j - x_k), c_j = y_j/d_j, (3) out = Σ_j c_j q_j with a warp-shuffle
+// reduction per coefficient.  A repeated node gives d_j = 0: the reference's `/` panics → flag.
+template <class F>
+__global__ void __launch_bounds__(1024)
+interp_master_kernel(const F f, const u64* __restrict__ xs, u32 k, u64* __restrict__ m0, u64* __restrict__ m1) {
+  // m0/m1: k+1 words each, ping-pong; the result ends in (k odd ? m1 : m0)
+  const u32 t = threadIdx.x;
+  for (u32 i = t; i <= k; i += blockDim.x) m0[i] = (i == 0) ? 1 % f.modulus() : 0ULL;
+  __syncthreads();
+  u64* cur = m0;
+  u64* nxt = m1;
+  for (u32 s = 0; s < k; s++) {  // cur has degree s; nxt = cur · (X - x_s)
+    const u64 x = xs[s];
+    for (u32 i = t; i <= s + 1; i += blockDim.x) {
+      const u64 lo = (i >= 1) ? cur[i - 1] : 0ULL;
+      const u64 hi = (i <= s) ? f.mul(cur[i], x) : 0ULL;
+      nxt[i] = f.sub(lo, hi);
+    }
+    __syncthreads();
+    u64* tmp = cur; cur = nxt; nxt = tmp;
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(256)
+interp_nodes_kernel(const F f, const u64* __restrict__ M, const u64* __restrict__ xs, const u64* __restrict__ ys, u32 k,
+                    u64* __restrict__ partial /* [ceil(k/32)][k] */, int* flag) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = j < k;
+  const u64 x = live ? xs[j] : 0ULL;
+  // pass 1: d_j = q_j(x_j), with q_j[i-1] = M[i] + x_j·q_j[i], q_j[k-1] = M[k] = 1, Horner from the top
+  u64 qv = 0, d = 0;
+  for (u32 i = k; i >= 1; i--) {
+    qv = f.add(M[i], f.mul(qv, x));  // q_j[i-1]
+    d = f.add(f.mul(d, x), qv);
+  }
+  u64 c = 0;
+  if (live) {
+    if (d == 0) atomicExch(flag, 1);
+    else c = f.mul(ys[j], field_pow(f, d, f.modulus() - 2));
+  }
+  // pass 2: Σ over the warp's nodes of c_j · q_j[i-1]
+  const u32 warp = j >> 5, lane = threadIdx.x & 31;
+  qv = 0;
+  for (u32 i = k; i >= 1; i--) {
+    qv = f.add(M[i], f.mul(qv, x));
+    u64 term = f.mul(c, qv);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) term = f.add(term, __shfl_down_sync(0xFFFFFFFFu, term, off));
+    if (lane == 0) partial[(size_t)warp * k + (i - 1)] = term;
+  }
+}
+
+template <class F>
+__global__ void interp_sum_kernel(const F f, const u64* __restrict__ partial, u32 k, u32 nwarps, u64* __restrict__ out) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  u64 acc = 0;
+  for (u32 w = 0; w < nwarps; w++) acc = f.add(acc, partial[(size_t)w * k + i]);
+  out[i] = acc;
+}
+
+template <class F>
+static int interp_with_field(ronk_ctx* ctx, const F& f, const u64* xs, const u64* ys, u32 k, u64* out) {
+  const u32 blocks = (k + 255) / 256, nwarps = blocks * 8;
+  const size_t words = 2 * (size_t)(k + 1) + (size_t)nwarps * k;
+  RONK_TRY(ensure_ws(ctx, &ctx->ws2, &ctx->ws2_bytes, words * sizeof(u64)));
+  u64* m0 = (u64*)ctx->ws2;
+  u64* m1 = m0 + (k + 1);
+  u64* partial = m1 + (k + 1);
+  RONK_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+  {
+    LaunchScope ls(ctx, "interp_master");
+    interp_master_kernel<F><<<1, 1024, 0, ctx->stream>>>(f, xs, k, m0, m1);
+  }
+  RONK_TRY(check_launch(ctx, "interp_master_kernel"));
+  const u64* M = (k & 1) ? m1 : m0;
+  {
+    LaunchScope ls(ctx, "interp_nodes");
+    interp_nodes_kernel<F><<<blocks, 256, 0, ctx->stream>>>(f, M, xs, ys, k, partial, ctx->d_flag);
+  }
+  RONK_TRY(check_launch(ctx, "interp_nodes_kernel"));
+  {
+    LaunchScope ls(ctx, "interp_sum");
+    interp_sum_kernel<F><<<(k + 255) / 256, 256, 0, ctx->stream>>>(f, partial, k, nwarps, out);
+  }
+  return check_launch(ctx, "interp_sum_kernel");
+}
+
 __global__ void pad_copy_kernel(u64* dst, const u64* src, size_t len, size_t n) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (i < len) ? src[i] : 0ULL;
@@ -539,6 +634,32 @@ int ronk_poly_lagrange_eval_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, cons
   }
   RONK_TRY(check_launch(ctx, "lagrange_eval_kernel"));
   return down(ctx, out, O.p, 1);
+}
+
+int ronk_poly_interpolate_u64_host(ronk_ctx* ctx, uint64_t p, const uint64_t* xs, const uint64_t* ys, size_t k,
+                                   uint64_t* out) {
+  if (!ctx || (k && (!xs || !ys || !out))) return set_err(ctx, RONK_EINVAL, "null argument");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (k == 0) return RONK_OK;
+  if (k > 8192) return set_err(ctx, RONK_EUNSUPPORTED, "more than 8192 nodes (O(K²) interpolation)");
+  for (size_t i = 0; i < k; i++)
+    if (xs[i] >= p || ys[i] >= p) return set_err(ctx, RONK_EINVAL, "non-canonical residue");
+  DevBuf X, Y, O;
+  RONK_TRY(up(ctx, &X.p, xs, k));
+  RONK_TRY(up(ctx, &Y.p, ys, k));
+  RONK_CUDA(ctx, cudaMalloc((void**)&O.p, k * sizeof(u64)));
+  if (p == GL_P) {
+    GoldilocksField f;
+    RONK_TRY(interp_with_field(ctx, f, X.p, Y.p, (u32)k, O.p));
+  } else {
+    MontField f;
+    RONK_TRY(make_mont_field(ctx, p, 0, false, &f));
+    RONK_TRY(interp_with_field(ctx, f, X.p, Y.p, (u32)k, O.p));
+  }
+  RONK_CUDA(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_TRY(down(ctx, out, O.p, k));
+  if (*ctx->h_flag) return set_err(ctx, RONK_EINVAL, "interpolation: repeated x coordinate (the reference divides by zero)");
+  return RONK_OK;
 }
 
 int ronk_poly_divrem_u64_host(ronk_ctx* ctx, uint64_t p, const uint64_t* a, size_t da, const uint64_t* b, size_t db,

@@ -115,6 +115,43 @@ def test_div_by_linear_factor_scan_vs_oracle_and_identity():
         c.call("ronk_poly_div_linear_u64", GL, A.data_ptr(), d, b0, b1, A.data_ptr(), R.data_ptr())
 
 
+def test_reed_solomon_decode_interpolation(kats):
+    """§8f row 2: Message::decode (codes/reed_solomon.rs:55-107) = interpolation through the first K
+    coordinates.  Reference decode tests, the literal oracle at small K, the inverse transform on a full
+    set of roots of unity, and evaluate∘interpolate = id at K = 4097."""
+    from ronkathon_b200 import GoldilocksField, PlutoBaseField, Polynomial, PrimeField, RonkPanic, codes
+    ctx()
+    r = kats["reed_solomon_decode"]
+    F127 = PrimeField(127)
+    for msg in r["messages"]:                                            # reed_solomon.rs:177-219
+        cw = codes.rs_encode(msg, r["n"], F127)
+        assert [v.value for v in codes.rs_decode(cw, len(msg), F127)] == msg
+    rng = np.random.default_rng(21)
+    for F, p in ((F127, 127), (PlutoBaseField, 101), (GoldilocksField, GL)):
+        for k in (1, 2, 3, 6, 10):
+            xs = [int(v) for v in (rng.choice(p, size=k, replace=False) if p < 1000 else oracle.splitmix(p, 50 + k, k))]
+            ys = [int(v) for v in oracle.splitmix(p, 60 + k, k)]
+            got = codes.rs_decode(list(zip(xs, ys)), k, F)
+            assert [v.value for v in got] == [int(v) for v in oracle.rs_decode(p, xs, ys, k)], (p, k)
+    for n in (256, 2048):                                                # full root-of-unity set: ifft
+        msg = oracle.splitmix(GL, n, n)
+        w = oracle.root_of_unity(GL, n)
+        xs = np.array([pow(w, i, GL) for i in range(n)], dtype=np.uint64)
+        ys = oracle.ntt_fast(GL, msg)
+        got = codes.rs_decode(list(zip(xs.tolist(), ys.tolist())), n, GoldilocksField)
+        assert np.array_equal(np.array([v.value for v in got], dtype=np.uint64), msg), n
+    k = 4097                                                             # multi-block, odd K
+    xs, ys = oracle.splitmix(GL, 71, k), oracle.splitmix(GL, 72, k)
+    assert len(set(xs.tolist())) == k
+    coeffs = [v.value for v in codes.rs_decode(list(zip(xs.tolist(), ys.tolist())), k, GoldilocksField)]
+    for i in (0, 1, 31, 32, 255, 256, 2048, 4095, 4096):
+        assert oracle.poly_eval_horner(GL, coeffs, int(xs[i])) == int(ys[i]), i
+    back = Polynomial(coeffs, GoldilocksField).evaluate_many(xs.tolist())
+    assert [v.value for v in back] == ys.tolist()
+    with pytest.raises(RonkPanic):
+        codes.rs_decode([(1, 3), (1, 4), (2, 5)], 3, F127)               # repeated x: the reference divides by zero
+
+
 def test_kzg_open_at_scale_matches_fast_oracle():
     """commit→open on the device at a size the reference's const-generic arrays cannot reach:
     2^16 F17 coefficients, quotient by the scan kernel, commitment by the bucket MSM."""

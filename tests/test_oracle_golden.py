@@ -148,6 +148,21 @@ def test_kzg_kats(kats):
         oracle.commit([1] * 8, g1)
 
 
+def test_reed_solomon_decode_kats(kats):
+    """decoding / decoding_longer_message (src/codes/reed_solomon.rs:177-219): encode to N = 7, decode the
+    first K coordinates with the literal combination formula (:55-107)."""
+    r = kats["reed_solomon_decode"]
+    for msg in r["messages"]:
+        xs, ys = oracle.rs_encode(r["p"], msg, r["n"])
+        assert list(oracle.rs_decode(r["p"], xs, ys, len(msg))) == msg
+    # on a full set of roots of unity the interpolant is the inverse transform
+    msg = oracle.splitmix(GL, 3, 8)
+    xs, ys = oracle.rs_encode(GL, msg, 8)
+    assert np.array_equal(oracle.rs_decode(GL, xs, ys, 8), msg) and np.array_equal(oracle.ifft(GL, ys), msg)
+    with pytest.raises(oracle.OraclePanic):
+        oracle.rs_decode(127, [1, 1, 2], [3, 4, 5], 3)   # repeated x: division by zero
+
+
 def test_reed_solomon_kat(kats):
     r = kats["reed_solomon"]
     xs, ys = oracle.rs_encode(r["p"], r["msg"], r["n"])
