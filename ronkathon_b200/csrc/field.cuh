@@ -41,6 +41,40 @@ constexpr u64 GL_EPS = 0xFFFFFFFFULL;  // 2^64 mod p
 // ------------------------------------------------------------------------------------------
 // Goldilocks
 // ------------------------------------------------------------------------------------------
+// Correction tail "(hi:lo) -= EPS·borrow" with m = 0 / 0xFFFFFFFF the borrow mask.  Two forms:
+//   sub-family: lo -= m (borrow out), hi -= borrow       → IADD3 + IADD3.X (both on the ALU pipe)
+//   add-family: (hi:lo) += (m : m·m), m·m = 0 / 1        → IMAD + IADD3 + IMAD.X (one ALU op)
+// The butterfly network is throttled by the ALU pipe while the FMA pipe idles, so the longer
+// add-family form is the faster one where ptxas keeps it on the FMA pipe.  RONK_FMA_TAIL selects it
+// per operation: bit 0 sub, bit 1 add, bit 2 both reduce tails, bit 3 / bit 4 first / second reduce
+// tail only.  Measured on B200 (2^24 transform): 0 → 0.437 ms, 1 → 0.421, 2 → 0.424, 3 → 0.411,
+// 4 → 0.427, 7 → 0.418, 11 / 19 → 0.411; 3 is the default.
+#ifndef RONK_FMA_TAIL
+#define RONK_FMA_TAIL 3
+#endif
+#define RONK_TAIL_SUBFAM(lo, hi) "sub.cc.u32 " lo ", " lo ", m;\n\t" "subc.u32 " hi ", " hi ", 0;\n\t"
+#define RONK_TAIL_ADDFAM(lo, hi) \
+  "mul.lo.u32 bw, m, m;\n\t" "add.cc.u32 " lo ", " lo ", bw;\n\t" "madc.lo.u32 " hi ", m, 1, " hi ";\n\t"
+#if RONK_FMA_TAIL & 1
+#define RONK_TAIL_SUB(lo, hi) RONK_TAIL_ADDFAM(lo, hi)
+#else
+#define RONK_TAIL_SUB(lo, hi) RONK_TAIL_SUBFAM(lo, hi)
+#endif
+#if RONK_FMA_TAIL & 2
+#define RONK_TAIL_ADD(lo, hi) RONK_TAIL_ADDFAM(lo, hi)
+#else
+#define RONK_TAIL_ADD(lo, hi) RONK_TAIL_SUBFAM(lo, hi)
+#endif
+#if RONK_FMA_TAIL & (4 | 8)
+#define RONK_TAIL_RED1(lo, hi) RONK_TAIL_ADDFAM(lo, hi)
+#else
+#define RONK_TAIL_RED1(lo, hi) RONK_TAIL_SUBFAM(lo, hi)
+#endif
+#if RONK_FMA_TAIL & (4 | 16)
+#define RONK_TAIL_RED2(lo, hi) RONK_TAIL_ADDFAM(lo, hi)
+#else
+#define RONK_TAIL_RED2(lo, hi) RONK_TAIL_SUBFAM(lo, hi)
+#endif
 struct GoldilocksField {
   RONK_HD u64 modulus() const { return GL_P; }
 
@@ -51,12 +85,11 @@ struct GoldilocksField {
   //   add: a + b = a - (p - b); p - b ∈ [1, p] and sub(a, p) = a still holds (borrow path).
   static __device__ __forceinline__ u64 sub_words(u32 a0, u32 a1, u32 b0, u32 b1) {
     u32 d0, d1;
-    asm("{\n\t.reg .u32 m;\n\t"
+    asm("{\n\t.reg .u32 m, bw;\n\t"
         "sub.cc.u32 %0, %2, %4;\n\t"
         "subc.cc.u32 %1, %3, %5;\n\t"
         "subc.u32 m, 0, 0;\n\t"        // m = -borrow = EPS·borrow
-        "sub.cc.u32 %0, %0, m;\n\t"
-        "subc.u32 %1, %1, 0;\n\t}"
+        RONK_TAIL_SUB("%0", "%1") "}"
         : "=&r"(d0), "=&r"(d1)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
     return ((u64)d1 << 32) | d0;
@@ -68,14 +101,13 @@ struct GoldilocksField {
   // does NOT carry (then +p, i.e. -EPS).  b + EPS < 2^64 because b < p.  Add-family carries only.
   __device__ __forceinline__ u64 add(u64 a, u64 b) const {
     u32 s0, s1;
-    asm("{\n\t.reg .u32 t0, t1, m;\n\t"
+    asm("{\n\t.reg .u32 t0, t1, m, bw;\n\t"
         "add.cc.u32 t0, %4, 0xFFFFFFFF;\n\t"
         "addc.u32 t1, %5, 0;\n\t"
         "add.cc.u32 %0, %2, t0;\n\t"
         "addc.cc.u32 %1, %3, t1;\n\t"
         "addc.u32 m, 0xFFFFFFFF, 0;\n\t"      // carry - 1: 0 or 0xFFFFFFFF (= EPS·borrow)
-        "sub.cc.u32 %0, %0, m;\n\t"
-        "subc.u32 %1, %1, 0;\n\t}"
+        RONK_TAIL_ADD("%0", "%1") "}"
         : "=&r"(s0), "=&r"(s1)
         : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
     return ((u64)s1 << 32) | s0;
@@ -89,19 +121,17 @@ struct GoldilocksField {
     u32 z0, z1;
     // second step: t - (p - W) ≡ t + (r1 : 0xFFFFFFFF) (mod 2^64), and it borrows exactly when this
     // addition does NOT carry; m = carry - 1 is then the EPS mask of the "+p" correction.
-    asm("{\n\t.reg .u64 y;\n\t.reg .u32 y0, y1, m;\n\t"
+    asm("{\n\t.reg .u64 y;\n\t.reg .u32 y0, y1, m, bw;\n\t"
         "mad.wide.u32 y, %4, 0xFFFFFFFF, %6;\n\t"
         "mov.b64 {y0, y1}, y;\n\t"
         "sub.cc.u32 %0, y0, %5;\n\t"        // t = Y - r3
         "subc.cc.u32 %1, y1, 0;\n\t"
         "subc.u32 m, 0, 0;\n\t"
-        "sub.cc.u32 %0, %0, m;\n\t"
-        "subc.u32 %1, %1, 0;\n\t"
+        RONK_TAIL_RED1("%0", "%1")
         "add.cc.u32 %0, %0, 0xFFFFFFFF;\n\t" // t + (r1 : 0xFFFFFFFF)
         "addc.cc.u32 %1, %1, %3;\n\t"
         "addc.u32 m, 0xFFFFFFFF, 0;\n\t"     // carry - 1
-        "sub.cc.u32 %0, %0, m;\n\t"
-        "subc.u32 %1, %1, 0;\n\t}"
+        RONK_TAIL_RED2("%0", "%1") "}"
         : "=&r"(z0), "=&r"(z1)
         : "r"(r0), "r"(r1), "r"(r2), "r"(r3), "l"((u64)r0));
     return ((u64)z1 << 32) | z0;
@@ -109,14 +139,13 @@ struct GoldilocksField {
   // three-word form (r3 = 0): x = Y + W only
   static __device__ __forceinline__ u64 reduce_words3(u32 r0, u32 r1, u32 r2) {
     u32 z0, z1;
-    asm("{\n\t.reg .u64 y;\n\t.reg .u32 y0, y1, m;\n\t"
+    asm("{\n\t.reg .u64 y;\n\t.reg .u32 y0, y1, m, bw;\n\t"
         "mad.wide.u32 y, %4, 0xFFFFFFFF, %5;\n\t"
         "mov.b64 {y0, y1}, y;\n\t"
         "add.cc.u32 %0, y0, 0xFFFFFFFF;\n\t"
         "addc.cc.u32 %1, y1, %3;\n\t"
         "addc.u32 m, 0xFFFFFFFF, 0;\n\t"
-        "sub.cc.u32 %0, %0, m;\n\t"
-        "subc.u32 %1, %1, 0;\n\t}"
+        RONK_TAIL_RED2("%0", "%1") "}"
         : "=&r"(z0), "=&r"(z1)
         : "r"(r0), "r"(r1), "r"(r2), "l"((u64)r0));
     return ((u64)z1 << 32) | z0;
@@ -156,8 +185,9 @@ struct GoldilocksField {
     } else {
       const u32 a0 = (u32)a, a1 = (u32)(a >> 32);
       constexpr int s = S % 32;
-      // (y2:y1:y0) = a << s (96 bits), as a·2^s on the FMA pipe (two IMAD.WIDE) — the ALU pipe is
-      // the bottleneck of the butterfly network, the multiplier is not.
+      // (y2:y1:y0) = a << s (96 bits).  Written as a·2^s; ptxas turns the literal multiplier back into
+      // SHF/IMAD.SHL.  Keeping it opaque (constant memory) forces two half-rate IMAD.WIDE instead and
+      // was measured slower (0.422 vs 0.411 ms).
       u32 y0, y1, y2;
       if constexpr (s == 0) {
         y0 = a0; y1 = a1; y2 = 0u;
