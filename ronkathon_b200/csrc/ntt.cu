@@ -88,7 +88,16 @@ static int build_plan(ronk_ctx* ctx, const F& f, u64 p, u64 g, u32 log_n, NttPla
 }
 
 template <class F, int MODE, bool INV, int NTHR, int MINB>
-static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
+static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A0, u32 tiles, const char* name) {
+  NttTileArgs A = A0;
+  if (MODE == MODE_PASS1) {
+    static int pf = -1;  // RONK_PF_DIST: prefetch distance in units of co-resident CTAs (default 1, 0 = off)
+    if (pf < 0) {
+      const char* s = getenv("RONK_PF_DIST");
+      pf = s ? atoi(s) : 1;
+    }
+    A.prefetch_dist = (u32)pf * (u32)ctx->sm_count * (u32)MINB;
+  }
   const size_t smem = ((size_t)1 << A.tile_log) * sizeof(u64) + (size_t)A.tw_words * sizeof(u64) + 16;
   // set on every launch: the attribute is per device, and several contexts may live in one process
   RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_tile_kernel<F, MODE, INV, NTHR, MINB>,

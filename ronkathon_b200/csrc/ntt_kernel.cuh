@@ -39,6 +39,7 @@ struct NttTileArgs {
   const u64* tw_tile;  // per-round 2-D twiddle tables (see ntt_tw2d_layout), twiddle form
   u32 tw_off[4];       // start of round r's table inside tw_tile (in words)
   u32 tw_words;        // total words of tw_tile (even)
+  u32 prefetch_dist;   // pass 1: L2-prefetch the tile of CTA blockIdx.x + prefetch_dist (0 = off)
   const u64* tw_lo;    // PASS1: ω_n^x, x ∈ [0, 2^log_lo)
   const u64* tw_hi;    // PASS1: ω_n^(y·2^log_lo) (· n^-1 for the inverse), y ∈ [0, n >> log_lo)
   const u64* tw_hi_plain;  // PASS1: the same table without the n^-1 factor (twiddle stepping ratio)
@@ -193,6 +194,25 @@ RONK_DEV u32 ilog2(u32 v) {
   while ((1u << l) < v) l++;
   return l;
 }
+// Pass 1 runs one CTA per SM, so nothing overlaps a tile's strided load (4096 separate 8·C-byte
+// segments) with butterflies.  Each CTA therefore asks L2 to fetch the tile of the CTA that will
+// follow it on this SM (block index + number of co-resident CTAs); that load then hits L2.
+// Measured (2^24, B200): pass 1 0.245 → 0.234 ms at a distance of one wave (148 CTAs; 74–148 equal,
+// two or three waves slower than no prefetch).  The contiguous pass-2 tiles (two CTAs per SM already
+// overlap each other's phases) gain nothing from the same trick, so it is not done there.
+RONK_DEV void ntt_prefetch_pass1(const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
+#if defined(__CUDA_ARCH__)
+  const u32 kk = ilog2(nthr);
+  const u32 per_thread = (1u << A.tile_log) >> kk;
+  const u32 col = tid & ((1u << A.log_c) - 1u);
+  if (col & 3u) return;  // one request per 32-byte sector
+  const u32 b = tile / A.tiles_per_batch, sub = tile - b * A.tiles_per_batch;
+  const u64* base = A.src + ((u64)b << A.log_n) + ((u64)sub << A.log_c) + ((u64)(tid >> A.log_c) << A.log_n2) + col;
+  for (u32 j = 0; j < per_thread; j++)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((u64)((j << kk) >> A.log_c) << A.log_n2)));
+#endif
+}
+
 template <class F, int MODE>
 RONK_DEV void ntt_load_phase(u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
   const u32 T = 1u << A.tile_log;
@@ -693,6 +713,8 @@ __global__ void __launch_bounds__(NTHR, MINB) ntt_tile_kernel(const F f, const N
 #endif
   if ((RONK_LOAD_V0_MASK >> MODE) & 1) ntt_load_phase_v0<F, MODE>(smem, A, tile, tid, NTHR);
   else ntt_load_phase<F, MODE>(smem, A, tile, tid, NTHR);
+  if (MODE == MODE_PASS1 && A.prefetch_dist && tile + A.prefetch_dist < gridDim.x)
+    ntt_prefetch_pass1(A, tile + A.prefetch_dist, tid, NTHR);
   __syncthreads();
   if (use_tw) mbar_wait(bar, 0);
   u32 nst, wb, lcur;

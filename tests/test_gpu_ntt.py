@@ -128,6 +128,29 @@ def test_metric_size_2_24_bit_exact_and_properties():
     assert np.array_equal(host(s), host(ops.field_binop(c, "add", dev(X), b)))
 
 
+@pytest.mark.parametrize("log_n", [23, 25, 26])
+def test_largest_sizes(log_n):
+    """Up to the largest supported transform (2^26: N1 = N2 = 2^13, 13-bit sub-transforms in both passes,
+    512 MiB of data + 512 MiB workspace): X[k] = a(ω^k) at sampled k against the oracle's Horner
+    evaluation, full bit-exact comparison where the CPU transform is quick, and the round trip."""
+    from ronkathon_b200 import ops
+    c = ctx()
+    n = 1 << log_n
+    d = ops.splitmix_fill(c, n, 4242)
+    a = host(d).copy()
+    assert np.array_equal(a[:1000], oracle.splitmix(GL, 4242, 1000))
+    ops.ntt_(c, d, log_n)
+    X = host(d)
+    w = oracle.root_of_unity(GL, n)
+    for k in (0, 1, n // 2 + 3, (n // 3) | 1, n - 1):
+        assert int(X[k]) == oracle.poly_eval_horner(GL, a, oracle.pow_(GL, w, k)), (log_n, k)
+    if log_n <= 23:
+        assert np.array_equal(X, oracle.ntt_fast(GL, a))
+    ops.ntt_(c, d, log_n, inverse=True)
+    assert np.array_equal(host(d), a)
+    del d
+
+
 def test_fused_pointwise_multiply(gold64):
     from ronkathon_b200 import ops
     c = ctx()
