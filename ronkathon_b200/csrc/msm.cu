@@ -9,11 +9,16 @@
 //
 //   msm_bucket_kernel   every thread streams its share of (point, scalar) pairs into 16 private
 //                       buckets held in shared memory ([bucket][thread], conflict-free), then the
-//                       CTA tree-reduces each bucket across its threads → partial[cta][17].
-//   msm_finish_kernel   one CTA: per-bucket tree over the partials, then the running-sum
-//                       Σ s·B_s = Σ_{s=16..1} (B_16 + … + B_s), one affine point out.
-// The field is so small that an affine add costs one F101 inversion = x^99 (9 multiplies), cheaper
-// than projective formulas, and it keeps the reference's exceptional-case structure verbatim.
+//                       CTA tree-reduces the 16 × 128 partials with ALL threads sharing the
+//                       (bucket, pair) work of each level → partial[cta][17].
+//   msm_finish_kernel   one CTA, 64 threads per bucket: tree over the partials, then
+//                       Σ s·B_s = Σ_{k=1..16} (B_16 + … + B_k) as a suffix scan + tree sum in one warp.
+// The whole computation is a chain of dependent affine adds, so it is latency-bound: what matters is
+// the number of SEQUENTIAL adds (≈ 16 stream + 18 tree + 8 + 6 + 8 for 2^20 terms) and the latency of
+// one add.  The field is so small that an affine add costs one F101 inversion, cheaper than projective
+// formulas, and it keeps the reference's exceptional-case structure verbatim; in the MSM kernels the
+// inverse comes from a 101-entry table in shared memory (built per CTA with the x^99 chain) instead of
+// nine dependent multiplies per add.
 #include "ronk_internal.h"
 
 namespace ronk {
@@ -47,6 +52,12 @@ RONK_DEV Gf gf_mul(Gf a, Gf b) {
 // conj / norm, norm = a0² + 2a1²  (gf_101_2.rs:35-47); caller guarantees a != 0
 RONK_DEV Gf gf_inv(Gf a) {
   const u32 s = fq_inv((a.c0 * a.c0 + 2u * a.c1 * a.c1) % Q101);
+  return {fq_mul(a.c0, s), fq_mul(fq_neg(a.c1), s)};
+}
+
+// norm inverse from a table tab[a] = a^-1 mod 101 (a in 1..100)
+RONK_DEV Gf gf_inv_tab(Gf a, const uint8_t* tab) {
+  const u32 s = tab[(a.c0 * a.c0 + 2u * a.c1 * a.c1) % Q101];
   return {fq_mul(a.c0, s), fq_mul(fq_neg(a.c1), s)};
 }
 
@@ -92,15 +103,46 @@ RONK_DEV Pt pt_add(const Pt& a, const Pt& b) {
 }
 RONK_DEV u32 pt_add_w(u32 a, u32 b) { return pt_pack(pt_add(pt_unpack(a), pt_unpack(b))); }
 
+// Same addition law with the table inverse (MSM kernels).
+RONK_DEV u32 pt_add_t(u32 wa, u32 wb, const uint8_t* tab) {
+  if (wa == PT_INF) return wb;
+  if (wb == PT_INF) return wa;
+  const Pt a = pt_unpack(wa), b = pt_unpack(wb);
+  const bool same_x = gf_eq(a.x, b.x);
+  if (same_x && gf_eq(a.y, gf_neg(b.y))) return PT_INF;
+  Gf num, den;
+  if (same_x && gf_eq(a.y, b.y)) {
+    num = gf_mul(Gf{3, 0}, gf_mul(a.x, a.x));
+    den = gf_add(a.y, a.y);
+  } else {
+    num = gf_sub(b.y, a.y);
+    den = gf_sub(b.x, a.x);
+  }
+  const Gf lam = gf_mul(num, gf_inv_tab(den, tab));
+  Pt r;
+  r.inf = false;
+  r.x = gf_sub(gf_sub(gf_mul(lam, lam), a.x), b.x);
+  r.y = gf_sub(gf_mul(lam, gf_sub(a.x, r.x)), a.y);
+  return pt_pack(r);
+}
+RONK_DEV void build_inv_table(uint8_t* tab, u32 tid, u32 nthr) {
+  for (u32 a = tid; a < Q101; a += nthr) tab[a] = (uint8_t)(a ? fq_inv(a) : 0);
+}
+
 constexpr int MSM_THREADS = 128;
+constexpr int MSM_TERMS = 16;       // terms per thread the grid is sized for
+constexpr int MSM_FIN_LANES = 64;   // finishing threads per bucket
 
 __global__ void __launch_bounds__(MSM_THREADS) msm_bucket_kernel(const u32* __restrict__ points,
                                                                  const uint8_t* __restrict__ scalars, size_t n,
                                                                  u32* __restrict__ partial, int* flag) {
-  __shared__ u32 bucket[17][MSM_THREADS];
+  __shared__ u32 bucket[16][MSM_THREADS];  // bucket[s-1][thread]
+  __shared__ uint8_t inv[104];
   const u32 t = threadIdx.x;
+  build_inv_table(inv, t, MSM_THREADS);
 #pragma unroll
-  for (int s = 0; s < 17; s++) bucket[s][t] = PT_INF;
+  for (int s = 0; s < 16; s++) bucket[s][t] = PT_INF;
+  __syncthreads();
   const size_t stride = (size_t)gridDim.x * MSM_THREADS;
   bool bad = false;
   for (size_t i = (size_t)blockIdx.x * MSM_THREADS + t; i < n; i += stride) {
@@ -108,40 +150,55 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_bucket_kernel(const u32* __re
     const u32 s = scalars[i];
     if (s >= 17 || !pt_valid(w)) { bad = true; continue; }
     if (s == 0 || w == PT_INF) continue;  // g1 * 0 = Infinity (curve/mod.rs:163-165)
-    bucket[s][t] = pt_add_w(bucket[s][t], w);
+    bucket[s - 1][t] = pt_add_t(bucket[s - 1][t], w, inv);
   }
   if (bad) atomicExch(flag, 1);
   __syncthreads();
+  // 16 × len partial sums → 16 × len/2, every thread takes (bucket, pair) items: 8, 4, 2, 1, 1, 1, 1
+  // sequential adds instead of 16 per level on the surviving threads
   for (u32 half = MSM_THREADS / 2; half > 0; half >>= 1) {
-    if (t < half) {
-#pragma unroll 1
-      for (int s = 1; s < 17; s++) bucket[s][t] = pt_add_w(bucket[s][t], bucket[s][t + half]);
+    for (u32 idx = t; idx < 16u * half; idx += MSM_THREADS) {
+      const u32 s = idx / half, j = idx - s * half;
+      bucket[s][j] = pt_add_t(bucket[s][j], bucket[s][j + half], inv);
     }
     __syncthreads();
   }
-  if (t < 17) partial[(size_t)blockIdx.x * 17 + t] = bucket[t][0];
+  if (t < 17) partial[(size_t)blockIdx.x * 17 + t] = (t == 0) ? PT_INF : bucket[t - 1][0];
 }
 
-// partial[sets][17] → buckets_out[17], result.  blockDim = 17 warps.
-__global__ void __launch_bounds__(17 * 32) msm_finish_kernel(const u32* __restrict__ partial, u32 sets,
-                                                             u32* __restrict__ buckets_out, u32* __restrict__ result) {
-  __shared__ u32 B[17];
-  const u32 s = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  u32 acc = PT_INF;
-  for (u32 g = lane; g < sets; g += 32) acc = pt_add_w(acc, partial[(size_t)g * 17 + s]);
-  for (int off = 16; off > 0; off >>= 1) {
-    const u32 other = __shfl_down_sync(0xFFFFFFFFu, acc, off);
-    acc = pt_add_w(acc, other);
-  }
-  if (lane == 0) { B[s] = (s == 0) ? PT_INF : acc; buckets_out[s] = B[s]; }
+// partial[sets][17] → buckets_out[17], result.  blockDim = 16 buckets × MSM_FIN_LANES.
+__global__ void __launch_bounds__(16 * MSM_FIN_LANES) msm_finish_kernel(const u32* __restrict__ partial, u32 sets,
+                                                                        u32* __restrict__ buckets_out,
+                                                                        u32* __restrict__ result) {
+  __shared__ u32 red[16][MSM_FIN_LANES];
+  __shared__ uint8_t inv[104];
+  const u32 tid = threadIdx.x, s = tid / MSM_FIN_LANES, lane = tid % MSM_FIN_LANES;  // bucket s + 1
+  build_inv_table(inv, tid, blockDim.x);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    u32 run = PT_INF, tot = PT_INF;
-    for (int k = 16; k >= 1; k--) {
-      run = pt_add_w(run, B[k]);
-      tot = pt_add_w(tot, run);
+  u32 acc = PT_INF;
+  for (u32 g = lane; g < sets; g += MSM_FIN_LANES) acc = pt_add_t(acc, partial[(size_t)g * 17 + s + 1], inv);
+  red[s][lane] = acc;
+  __syncthreads();
+  for (u32 half = MSM_FIN_LANES / 2; half > 0; half >>= 1) {
+    if (lane < half) red[s][lane] = pt_add_t(red[s][lane], red[s][lane + half], inv);
+    __syncthreads();
+  }
+  if (tid < 17) buckets_out[tid] = (tid == 0) ? PT_INF : red[tid - 1][0];
+  if (tid < 32) {
+    // lane k < 16 holds B_{k+1}.  run_k = B_{k+1} + … + B_16 (suffix scan), result = Σ_k run_k:
+    // every B_s is counted s times.  8 sequential adds instead of the 32 of the serial running sum.
+    u32 v = (tid < 16) ? red[tid][0] : PT_INF;
+#pragma unroll
+    for (int off = 1; off < 16; off <<= 1) {
+      const u32 other = __shfl_down_sync(0xFFFFFFFFu, v, off);
+      if (tid + off < 16) v = pt_add_t(v, other, inv);
     }
-    result[0] = tot;
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) {
+      const u32 other = __shfl_down_sync(0xFFFFFFFFu, v, off);
+      if (tid < (u32)off) v = pt_add_t(v, other, inv);
+    }
+    if (tid == 0) result[0] = v;
   }
 }
 
@@ -173,8 +230,8 @@ __global__ void point_op_kernel(int op, const u32* a, const u32* b, const uint8_
 }
 
 static int msm_grid(ronk_ctx* ctx, size_t n) {
-  size_t ctas = (n + (size_t)MSM_THREADS * 32 - 1) / ((size_t)MSM_THREADS * 32);
-  const size_t cap = (size_t)ctx->sm_count * 4;
+  size_t ctas = (n + (size_t)MSM_THREADS * MSM_TERMS - 1) / ((size_t)MSM_THREADS * MSM_TERMS);
+  const size_t cap = (size_t)ctx->sm_count * 8;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
   return (int)ctas;
@@ -201,7 +258,7 @@ static int msm_device(ronk_ctx* ctx, const uint8_t* points, size_t n_points, con
   RONK_TRY(check_launch(ctx, "msm_bucket_kernel"));
   {
     LaunchScope ls(ctx, "msm_finish");
-    msm_finish_kernel<<<1, 17 * 32, 0, ctx->stream>>>(partial, (u32)ctas, d_buckets, d_result);
+    msm_finish_kernel<<<1, 16 * MSM_FIN_LANES, 0, ctx->stream>>>(partial, (u32)ctas, d_buckets, d_result);
   }
   RONK_TRY(check_launch(ctx, "msm_finish_kernel"));
   u32 host[18];
@@ -273,7 +330,7 @@ int ronk_msm_combine_buckets_host(ronk_ctx* ctx, const uint8_t* buckets, size_t 
   if (words) RONK_CUDA(ctx, cudaMemcpyAsync(partial, buckets, words * 4, cudaMemcpyHostToDevice, ctx->stream));
   {
     LaunchScope ls(ctx, "msm_finish");
-    msm_finish_kernel<<<1, 17 * 32, 0, ctx->stream>>>(partial, (u32)n_sets, d_buckets, d_result);
+    msm_finish_kernel<<<1, 16 * MSM_FIN_LANES, 0, ctx->stream>>>(partial, (u32)n_sets, d_buckets, d_result);
   }
   RONK_TRY(check_launch(ctx, "msm_finish_kernel"));
   u32 res;
