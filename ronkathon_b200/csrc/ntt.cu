@@ -146,15 +146,25 @@ static int launch_tile(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tile
   return launch_tile_n<F, MODE, INV, 32, 2>(ctx, f, A, tiles, name);
 }
 
+// src == nullptr: in place.  Otherwise (batch == 1) the transform reads src[0, src_len) zero-extended to n
+// words and writes data[0, dst_len): the zero padding of poly_mul's operands and the clipping of its
+// result happen inside the load / store phases instead of in separate copy kernels.
 template <class F, bool INV>
-static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, const u64* mul, u32 batch) {
+static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, const u64* mul, u32 batch,
+                   const u64* src = nullptr, u64 src_len = NTT_UNBOUNDED, u64 dst_len = NTT_UNBOUNDED) {
   const u32 log_n = pl.log_n;
   u64 tiles = 0;
+  if (!src) src = data;
+  if (src_len >= ((u64)1 << log_n)) src_len = NTT_UNBOUNDED;
+  if (dst_len >= ((u64)1 << log_n)) dst_len = NTT_UNBOUNDED;
   if (!pl.two_pass) {
     u32 cap = 12;
     if (const char* s = getenv("RONK_SINGLE_TILE_LOG")) cap = (u32)atoi(s);
-    const NttTileArgs A =
+    NttTileArgs A =
         ntt_args_single(data, mul, pl.tw1_2d[INV ? 1 : 0], pl.scale_inv, log_n, (u64)batch << log_n, INV, cap, &tiles);
+    A.src = src;
+    A.src_len = src_len;
+    A.dst_len = dst_len;
     if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
     return launch_tile<F, MODE_SINGLE, INV>(ctx, f, A, (u32)tiles, INV ? "intt_single" : "ntt_single");
   }
@@ -170,19 +180,22 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
   u32 tile1, tile2;
   ntt_pass_tiles(log_n, (u32)pref1, (u32)pref2, &tile1, &tile2);
   // pass 1: N1-point transforms down the columns, inter-pass twiddle, blocked write to the workspace
-  const NttTileArgs A1 = ntt_args_pass1(data, (u64*)ctx->ws, pl.tw1_2d[INV ? 1 : 0], pl.tw_lo, INV ? pl.tw_hi_inv : pl.tw2, pl.tw2,
-                                        log_n, batch, tile1, tile2, &tiles);
+  NttTileArgs A1 = ntt_args_pass1(src, (u64*)ctx->ws, pl.tw1_2d[INV ? 1 : 0], pl.tw_lo, INV ? pl.tw_hi_inv : pl.tw2, pl.tw2,
+                                  log_n, batch, tile1, tile2, &tiles);
+  A1.src_len = src_len;
   if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
   RONK_TRY((launch_tile<F, MODE_PASS1, INV>(ctx, f, A1, (u32)tiles, INV ? "intt_pass1" : "ntt_pass1")));
   // pass 2: N2-point transforms along the contiguous workspace tiles, natural-order output
-  const NttTileArgs A2 = ntt_args_pass2((const u64*)ctx->ws, data, mul, pl.tw2_2d[INV ? 1 : 0], log_n, batch, tile2, &tiles);
+  NttTileArgs A2 = ntt_args_pass2((const u64*)ctx->ws, data, mul, pl.tw2_2d[INV ? 1 : 0], log_n, batch, tile2, &tiles);
+  A2.dst_len = dst_len;
   if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
   return launch_tile<F, MODE_PASS2, INV>(ctx, f, A2, (u32)tiles, INV ? "intt_pass2" : "ntt_pass2");
 }
 
 template <class F>
 static int ntt_with_field(ronk_ctx* ctx, const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 log_n, u32 batch,
-                          int inverse) {
+                          int inverse, const u64* src = nullptr, u64 src_len = NTT_UNBOUNDED,
+                          u64 dst_len = NTT_UNBOUNDED) {
   auto key = std::make_tuple((uint64_t)p, (uint64_t)g, (uint32_t)log_n);
   auto it = ctx->plans.find(key);
   if (it == ctx->plans.end()) {
@@ -190,8 +203,24 @@ static int ntt_with_field(ronk_ctx* ctx, const F& f, u64 p, u64 g, u64* data, co
     RONK_TRY(build_plan(ctx, f, p, g, log_n, &pl));
     it = ctx->plans.emplace(key, pl).first;
   }
-  return inverse ? run_ntt<F, true>(ctx, f, it->second, data, mul, batch)
-                 : run_ntt<F, false>(ctx, f, it->second, data, mul, batch);
+  return inverse ? run_ntt<F, true>(ctx, f, it->second, data, mul, batch, src, src_len, dst_len)
+                 : run_ntt<F, false>(ctx, f, it->second, data, mul, batch, src, src_len, dst_len);
+}
+
+// One transform, out of place: dst[0, dst_len) = NTT(src[0, src_len) zero-extended to 2^log_n) [⊙ mul].
+// log_n >= 1; dst needs only dst_len words.  Used by poly_mul (poly.cu).
+int ntt_device_bounded(ronk_ctx* ctx, u64 p, u64 g, const u64* src, u64 src_len, u64* dst, u64 dst_len, const u64* mul,
+                       u32 log_n, int inverse) {
+  if (!ctx || !src || !dst) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (log_n == 0 || log_n > 26 || (p - 1) % ((u64)1 << log_n) != 0)
+    return set_err(ctx, RONK_EINVAL, "unsupported transform size");
+  if (is_goldilocks_fast(p, g)) {
+    GoldilocksField f;
+    return ntt_with_field(ctx, f, p, g, dst, mul, log_n, 1, inverse, src, src_len, dst_len);
+  }
+  MontField f;
+  RONK_TRY(make_mont_field(ctx, p, g, inverse != 0, &f));
+  return ntt_with_field(ctx, f, p, g, dst, mul, log_n, 1, inverse, src, src_len, dst_len);
 }
 
 int ntt_device(ronk_ctx* ctx, u64 p, u64 g, u64* data, const u64* mul, u32 log_n, u32 batch, int inverse) {

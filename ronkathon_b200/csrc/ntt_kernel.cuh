@@ -40,6 +40,10 @@ struct NttTileArgs {
   u32 tw_off[4];       // start of round r's table inside tw_tile (in words)
   u32 tw_words;        // total words of tw_tile (even)
   u32 prefetch_dist;   // pass 1: L2-prefetch the tile of CTA blockIdx.x + prefetch_dist (0 = off)
+  // Bounded transforms (batch == 1 only; poly_mul): words of src at index >= src_len read as zero (the
+  // zero padding of a shorter operand), words of dst at index >= dst_len are not written (a product with
+  // fewer than n coefficients).  NTT_UNBOUNDED = no bound; the unbounded loops are separate code.
+  u64 src_len, dst_len;
   const u64* tw_lo;    // PASS1: ω_n^x, x ∈ [0, 2^log_lo)
   const u64* tw_hi;    // PASS1: ω_n^(y·2^log_lo) (· n^-1 for the inverse), y ∈ [0, n >> log_lo)
   const u64* tw_hi_plain;  // PASS1: the same table without the n^-1 factor (twiddle stepping ratio)
@@ -178,6 +182,17 @@ RONK_DEV void ntt_round(const F& f, u64* smem, const u64* tw, const NttTileArgs&
 }
 
 // ---------------- load phase: HBM → shared ----------------
+// Which formulation of the load/store phases each mode uses (bit MODE set → per-element index
+// math "v0", clear → XOR-composed addresses).  Measured on B200 (2^24, profiles/): the XOR-composed
+// phases win for the strided pass 1 (0.287 → 0.267 ms); for the contiguous pass 2 the per-element
+// form is faster (0.197 vs 0.214 ms).  tests/emu follows the same selection.
+#ifndef RONK_LOAD_V0_MASK
+#define RONK_LOAD_V0_MASK 5
+#endif
+#ifndef RONK_STORE_V0_MASK
+#define RONK_STORE_V0_MASK 5
+#endif
+
 // Loads are issued LD_BATCH at a time into registers before any is stored, so the HBM latency of a
 // tile is paid once per batch, not once per element.  nthr is a power of two, so the tile index of
 // the j-th element of a thread is e = tid | (j·nthr): disjoint bit sets.  The swizzle is XOR-linear,
@@ -213,6 +228,8 @@ RONK_DEV void ntt_prefetch_pass1(const NttTileArgs& A, u32 tile, u32 tid, u32 nt
 #endif
 }
 
+constexpr u64 NTT_UNBOUNDED = ~0ULL;
+
 template <class F, int MODE>
 RONK_DEV void ntt_load_phase(u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
   const u32 T = 1u << A.tile_log;
@@ -230,6 +247,17 @@ RONK_DEV void ntt_load_phase(u64* smem, const NttTileArgs& A, u32 tile, u32 tid,
   else gaddr_t = ((u64)b << A.log_n) + ((u64)sub << A.tile_log) + tid;
   const u32 sw_t = swz(tid);
   const u32 per_thread = T >> kk;  // elements per thread (T ≥ nthr)
+  if (A.src_len != NTT_UNBOUNDED) {  // zero-padded operand (batch == 1): same map, bounds-checked loads
+    for (u32 j = 0; j < per_thread; j++) {
+      const u32 gj = j << kk;
+      u64 g;
+      if (MODE == MODE_PASS1) g = gaddr_t + ((u64)(gj >> A.log_c) << A.log_n2);
+      else g = gaddr_t + gj;
+      const bool ok = g < A.src_len && (MODE != MODE_SINGLE || g < A.total);
+      smem[sw_t ^ swz(gj)] = ok ? A.src[g] : 0ULL;
+    }
+    return;
+  }
   for (u32 j0 = 0; j0 < per_thread; j0 += LD_BATCH) {
     u64 v[LD_BATCH];
 #pragma unroll
@@ -324,7 +352,7 @@ RONK_DEV void ntt_store_phase(const F& f, const u64* smem, const NttTileArgs& A,
     for (u32 j = 0; j < per_thread; j++) {
       const u32 gj = j << kk;
       const u64 ga = base_t + gj;
-      if (ga >= A.total) continue;
+      if (ga >= A.total || ga >= A.dst_len) continue;
       u64 v = smem[sw_t ^ swz(store_perm<MODE>(A, gj))];
       if (A.flags & NTT_FLAG_SCALE) v = f.mul_tw(v, A.scale);
       if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[ga]);
@@ -382,6 +410,7 @@ RONK_DEV void ntt_store_phase(const F& f, const u64* smem, const NttTileArgs& A,
     for (u32 j = 0; j < per_thread; j++) {
       const u32 gj = j << kk;  // kk ≥ lc2: gj carries no k1_in bits
       const u64 addr = addr_t + ((u64)(gj >> lc2) << A.log_n1);
+      if (addr >= A.dst_len) continue;
       u64 v = smem[sw_t ^ swz(store_perm<MODE>(A, gj))];
       if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[addr]);
       A.dst[addr] = v;
@@ -411,10 +440,11 @@ RONK_DEV void ntt_load_phase_v0(u64* smem, const NttTileArgs& A, u32 tile, u32 t
       const u32 e = e0 + i * nthr;
       if (MODE == MODE_SINGLE) {
         const u64 g = base + e;
-        v[i] = (e < T && g < A.total) ? A.src[g] : 0ULL;
+        v[i] = (e < T && g < A.total && g < A.src_len) ? A.src[g] : 0ULL;
       } else if (MODE == MODE_PASS1) {
         const u32 j1 = e >> A.log_c, c = e & cmask;
-        v[i] = (e < T) ? A.src[base + ((u64)j1 << A.log_n2) + c] : 0ULL;
+        const u64 g = base + ((u64)j1 << A.log_n2) + c;
+        v[i] = (e < T && g < A.src_len) ? A.src[g] : 0ULL;
       } else {
         v[i] = (e < T) ? A.src[base + e] : 0ULL;
       }
@@ -439,7 +469,7 @@ RONK_DEV void ntt_store_phase_v0(const F& f, const u64* smem, const NttTileArgs&
   if (MODE == MODE_SINGLE) {
     const u64 base = (u64)tile << A.tile_log;
     for (u32 g = tid; g < T; g += nthr) {
-      if (base + g >= A.total) continue;
+      if (base + g >= A.total || base + g >= A.dst_len) continue;
       const u32 bt = g >> A.log_m, k = g & (M - 1u);
       const u32 e = (bt << A.log_m) | bitrev(k, A.log_m);
       u64 v = smem[swz(e)];
@@ -469,6 +499,17 @@ RONK_DEV void ntt_store_phase_v0(const F& f, const u64* smem, const NttTileArgs&
   } else {
     const u32 lc2 = A.log_c;  // pass-2 tile: columns are the C2 adjacent k1 values
     const u64 base = ((u64)b << A.log_n) + ((u64)sub << lc2);
+    if (A.dst_len != NTT_UNBOUNDED) {  // clipped output (batch == 1); the unbounded loop below stays as it was
+      for (u32 g = tid; g < T; g += nthr) {
+        const u32 k2 = g >> lc2, k1_in = g & ((1u << lc2) - 1u);
+        const u64 addr = base + k1_in + ((u64)k2 << A.log_n1);
+        if (addr >= A.dst_len) continue;
+        u64 v = smem[swz((bitrev(k2, A.log_m) << lc2) | k1_in)];
+        if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[addr]);
+        A.dst[addr] = v;
+      }
+      return;
+    }
     for (u32 g = tid; g < T; g += nthr) {
       const u32 k2 = g >> lc2, k1_in = g & ((1u << lc2) - 1u);
       const u32 e = (bitrev(k2, A.log_m) << lc2) | k1_in;
@@ -508,6 +549,7 @@ inline NttTileArgs ntt_args_single(u64* data, const u64* mul, const u64* tw, u64
   if (tile_log > NTT_TILE_LOG_MAX) tile_log = NTT_TILE_LOG_MAX;
   A.src = data;
   A.dst = data;
+  A.src_len = A.dst_len = NTT_UNBOUNDED;
   A.tw_tile = tw;
   A.tw_words = ntt_tw2d_layout(log_n, A.tw_off);
   A.mul_src = mul;
@@ -534,6 +576,7 @@ inline NttTileArgs ntt_args_pass1(const u64* data, u64* ws, const u64* tw1, cons
   NttTileArgs A = {};
   A.src = data;
   A.dst = ws;
+  A.src_len = A.dst_len = NTT_UNBOUNDED;
   A.tw_tile = tw1;
   A.tw_words = ntt_tw2d_layout(sh.log_n1, A.tw_off);
   A.tw_lo = tw_lo;
@@ -557,6 +600,7 @@ inline NttTileArgs ntt_args_pass2(const u64* ws, u64* data, const u64* mul, cons
   NttTileArgs A = {};
   A.src = ws;
   A.dst = data;
+  A.src_len = A.dst_len = NTT_UNBOUNDED;
   A.tw_tile = tw2;
   A.tw_words = ntt_tw2d_layout(sh.log_n2, A.tw_off);
   A.mul_src = mul;
@@ -701,16 +745,6 @@ __global__ void __launch_bounds__(NTHR, MINB) ntt_tile_kernel(const F f, const N
     mbar_expect_tx(bar, A.tw_words * 8u);
     tma_bulk_g2s(tw, A.tw_tile, A.tw_words * 8u, bar);  // lands while the tile itself is being loaded
   }
-  // Which formulation of the load/store phases each mode uses (bit MODE set → per-element index
-  // math, clear → XOR-composed addresses).  Measured on B200 (2^24, profiles/): the XOR-composed
-  // phases win for the strided pass 1 (0.287 → 0.267 ms); for the contiguous pass 2 the per-element
-  // form is faster (0.197 vs 0.214 ms).
-#ifndef RONK_LOAD_V0_MASK
-#define RONK_LOAD_V0_MASK 5
-#endif
-#ifndef RONK_STORE_V0_MASK
-#define RONK_STORE_V0_MASK 5
-#endif
   if ((RONK_LOAD_V0_MASK >> MODE) & 1) ntt_load_phase_v0<F, MODE>(smem, A, tile, tid, NTHR);
   else ntt_load_phase<F, MODE>(smem, A, tile, tid, NTHR);
   if (MODE == MODE_PASS1 && A.prefetch_dist && tile + A.prefetch_dist < gridDim.x)

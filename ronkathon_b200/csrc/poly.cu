@@ -393,11 +393,6 @@ static int interp_with_field(ronk_ctx* ctx, const F& f, const u64* xs, const u64
   return check_launch(ctx, "interp_sum_kernel");
 }
 
-__global__ void pad_copy_kernel(u64* dst, const u64* src, size_t len, size_t n) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = (i < len) ? src[i] : 0ULL;
-}
-
 static int grid_for(ronk_ctx* ctx, size_t n, int threads) {
   size_t blocks = (n + threads - 1) / threads;
   size_t cap = (size_t)ctx->sm_count * 8;
@@ -425,20 +420,11 @@ static int poly_mul_with_field(ronk_ctx* ctx, const F& f, u64 p, u64 g, const u6
   RONK_TRY(ensure_ws(ctx, &ctx->ws2, &ctx->ws2_bytes, 2 * n * sizeof(u64)));
   u64* A = (u64*)ctx->ws2;
   u64* B = A + n;
-  {
-    LaunchScope ls(ctx, "pad_copy");
-    pad_copy_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(A, a, da, n);
-  }
-  {
-    LaunchScope ls(ctx, "pad_copy");
-    pad_copy_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(B, b, db, n);
-  }
-  RONK_TRY(check_launch(ctx, "pad_copy_kernel"));
-  RONK_TRY(ntt_device(ctx, p, g, A, nullptr, log_n, 1, 0));  // Â
-  RONK_TRY(ntt_device(ctx, p, g, B, A, log_n, 1, 0));        // B̂ ⊙ Â fused into the last stage
-  RONK_TRY(ntt_device(ctx, p, g, B, nullptr, log_n, 1, 1));  // back to coefficients
-  RONK_CUDA(ctx, cudaMemcpyAsync(c, B, L * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
-  return RONK_OK;
+  // the zero padding of a and b and the clipping of the product to L coefficients happen inside the
+  // transforms' load / store phases (no pad-copy kernels, no final device copy)
+  RONK_TRY(ntt_device_bounded(ctx, p, g, a, da, A, n, nullptr, log_n, 0));  // Â
+  RONK_TRY(ntt_device_bounded(ctx, p, g, b, db, B, n, A, log_n, 0));        // B̂ ⊙ Â fused into the last stage
+  return ntt_device_bounded(ctx, p, g, B, n, c, L, nullptr, log_n, 1);      // back to coefficients, L of them
 }
 
 static int poly_mul_device(ronk_ctx* ctx, u64 p, u64 g, const u64* a, size_t da, const u64* b, size_t db, u64* c) {

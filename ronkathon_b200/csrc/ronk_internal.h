@@ -139,5 +139,7 @@ int validate_modulus(ronk_ctx* ctx, u64 p);                                     
 
 // Internal device-pointer entry points used across translation units.
 int ntt_device(ronk_ctx* ctx, u64 p, u64 g, u64* data, const u64* mul, u32 log_n, u32 batch, int inverse);
+int ntt_device_bounded(ronk_ctx* ctx, u64 p, u64 g, const u64* src, u64 src_len, u64* dst, u64 dst_len, const u64* mul,
+                       u32 log_n, int inverse);
 
 }  // namespace ronk

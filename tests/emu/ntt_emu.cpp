@@ -59,22 +59,37 @@ std::vector<u64> table2d(const std::vector<u64>& tw1d, u32 log_m, bool inverse) 
   return out;
 }
 
+// 0: the kernel's own per-mode choice (RONK_LOAD_V0_MASK / RONK_STORE_V0_MASK), 1: XOR-composed phases
+// everywhere, 2: per-element ("v0") phases everywhere
+int g_variant = 0;
+bool use_v0(int mask, int mode) { return g_variant == 0 ? ((mask >> mode) & 1) != 0 : g_variant == 2; }
+
 template <class F, int MODE, bool INV>
 void run_tiles(const F& f, const NttTileArgs& A, u64 tiles) {
   const u32 T = 1u << A.tile_log, nthr = (T / 32 >= 32) ? T / 32 : 32;
   std::vector<u64> smem(T);
   for (u64 tile = 0; tile < tiles; tile++) {
-    for (u32 t = 0; t < nthr; t++) ntt_load_phase<F, MODE>(smem.data(), A, (u32)tile, t, nthr);
+    for (u32 t = 0; t < nthr; t++) {
+      if (use_v0(RONK_LOAD_V0_MASK, MODE)) ntt_load_phase_v0<F, MODE>(smem.data(), A, (u32)tile, t, nthr);
+      else ntt_load_phase<F, MODE>(smem.data(), A, (u32)tile, t, nthr);
+    }
     u32 nst, wb, lcur;
     for (u32 r = 0; ntt_round_plan(A, r, &nst, &wb, &lcur); r++)
       for (u32 t = 0; t < nthr; t++) ntt_round_dispatch<F, INV>(f, smem.data(), A.tw_tile, A, nst, wb, lcur, t, nthr);
-    for (u32 t = 0; t < nthr; t++) ntt_store_phase<F, MODE, INV>(f, smem.data(), A, (u32)tile, t, nthr);
+    for (u32 t = 0; t < nthr; t++) {
+      if (use_v0(RONK_STORE_V0_MASK, MODE)) ntt_store_phase_v0<F, MODE, INV>(f, smem.data(), A, (u32)tile, t, nthr);
+      else ntt_store_phase<F, MODE, INV>(f, smem.data(), A, (u32)tile, t, nthr);
+    }
   }
 }
 
+// src == nullptr: in place; otherwise the bounded out-of-place form of run_ntt() in ntt.cu (batch 1)
 template <class F, bool INV>
 int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 log_n, u32 batch, u32 tile_cap,
-        u32 pref1, u32 pref2) {
+        u32 pref1, u32 pref2, const u64* src = nullptr, u64 src_len = NTT_UNBOUNDED, u64 dst_len = NTT_UNBOUNDED) {
+  if (!src) src = data;
+  if (src_len >= ((u64)1 << log_n)) src_len = NTT_UNBOUNDED;
+  if (dst_len >= ((u64)1 << log_n)) dst_len = NTT_UNBOUNDED;
   const u64 n = (u64)1 << log_n;
   const u64 w = h_powmod(g, (p - 1) / n, p);
   const u64 ninv = h_powmod(n % p, p - 2, p);
@@ -85,6 +100,9 @@ int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 l
     auto tw1d = table(f, w, 1, n);
     auto tw = table2d(tw1d, log_n, INV);
     NttTileArgs A = ntt_args_single(data, mul, tw.data(), scale, log_n, (u64)batch << log_n, INV, tile_cap, &tiles);
+    A.src = src;
+    A.src_len = src_len;
+    A.dst_len = dst_len;
     run_tiles<F, MODE_SINGLE, INV>(f, A, tiles);
     return 0;
   }
@@ -98,10 +116,12 @@ int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 l
   ntt_pass_tiles(log_n, pref1, pref2, &tile1, &tile2);
   auto tw1_2d = table2d(tw1, sh.log_n1, INV);
   auto tw2_2d = table2d(tw2, sh.log_n2, INV);
-  NttTileArgs A1 = ntt_args_pass1(data, ws.data(), tw1_2d.data(), tw_lo.data(), INV ? tw_hi_inv.data() : tw2.data(),
+  NttTileArgs A1 = ntt_args_pass1(src, ws.data(), tw1_2d.data(), tw_lo.data(), INV ? tw_hi_inv.data() : tw2.data(),
                                   tw2.data(), log_n, batch, tile1, tile2, &tiles);
+  A1.src_len = src_len;
   run_tiles<F, MODE_PASS1, INV>(f, A1, tiles);
   NttTileArgs A2 = ntt_args_pass2(ws.data(), data, mul, tw2_2d.data(), log_n, batch, tile2, &tiles);
+  A2.dst_len = dst_len;
   run_tiles<F, MODE_PASS2, INV>(f, A2, tiles);
   return 0;
 }
@@ -122,6 +142,22 @@ int emu_ntt(uint64_t p, uint64_t g, uint64_t* data, const uint64_t* mul, uint32_
   MontField f = make_mont(p, g, inverse != 0);
   return inverse ? run<MontField, true>(f, p, g, false, data, mul, log_n, batch, tile_cap, pref1, pref2)
                  : run<MontField, false>(f, p, g, false, data, mul, log_n, batch, tile_cap, pref1, pref2);
+}
+
+void emu_set_variant(int v) { g_variant = v; }
+
+// Bounded out-of-place transform (ntt_device_bounded): dst[0, dst_len) = NTT(src[0, src_len) ‖ zeros) [⊙ mul].
+int emu_ntt_bounded(uint64_t p, uint64_t g, const uint64_t* src, uint64_t src_len, uint64_t* dst, uint64_t dst_len,
+                    const uint64_t* mul, uint32_t log_n, int inverse, uint32_t tile_cap, uint32_t pref1, uint32_t pref2) {
+  if (log_n == 0 || log_n > 26 || (p - 1) % ((u64)1 << log_n) != 0) return 1;
+  if (p == GL_P && g == 7) {
+    GoldilocksField f;
+    return inverse ? run<GoldilocksField, true>(f, p, g, true, dst, mul, log_n, 1, tile_cap, pref1, pref2, src, src_len, dst_len)
+                   : run<GoldilocksField, false>(f, p, g, true, dst, mul, log_n, 1, tile_cap, pref1, pref2, src, src_len, dst_len);
+  }
+  MontField f = make_mont(p, g, inverse != 0);
+  return inverse ? run<MontField, true>(f, p, g, false, dst, mul, log_n, 1, tile_cap, pref1, pref2, src, src_len, dst_len)
+                 : run<MontField, false>(f, p, g, false, dst, mul, log_n, 1, tile_cap, pref1, pref2, src, src_len, dst_len);
 }
 
 // Field-policy arithmetic, element-wise, for cross-checks against the oracle.

@@ -27,6 +27,8 @@ def emu():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src])
     lib = C.CDLL(so)
     lib.emu_ntt.argtypes = [C.c_uint64, C.c_uint64, P64, P64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.emu_ntt_bounded.argtypes = [C.c_uint64, C.c_uint64, P64, C.c_uint64, P64, C.c_uint64, P64, C.c_uint32, C.c_int,
+                                    C.c_uint32, C.c_uint32, C.c_uint32]
     lib.emu_field_op.argtypes = [C.c_uint64, C.c_int, P64, P64, P64, C.c_uint64, C.c_int]
     lib.emu_gl_w16.argtypes = [C.c_uint64, P64]
     lib.emu_swizzle_worst_conflict.argtypes = [C.c_uint32, C.c_uint32]
@@ -161,3 +163,46 @@ def test_emulated_two_pass_generic_and_fused_mul(emu, gold64):
     A10 = emu_ntt(emu, GL, 7, a10, 10)
     exp = np.array([oracle.mul(GL, int(x), int(y)) for x, y in zip(oracle.ntt_fast(GL, b10), A10)], dtype=np.uint64)
     assert np.array_equal(emu_ntt(emu, GL, 7, b10, 10, mul=A10), exp)
+
+
+def emu_ntt_bounded(emu, p, g, src, dst_len, log_n, inverse=False, mul=None, tile_cap=12, tiles=(13, 13)):
+    s = np.ascontiguousarray(src, dtype=np.uint64)
+    d = np.full(dst_len + 3, 0xDEADBEEF, dtype=np.uint64)   # 3 guard words past the clipped output
+    m = None if mul is None else np.ascontiguousarray(mul, dtype=np.uint64)
+    rc = emu.emu_ntt_bounded(p, g, _ptr(s), len(s), _ptr(d), dst_len, _ptr(m), log_n, int(inverse), tile_cap, tiles[0],
+                             tiles[1])
+    assert rc == 0 and np.all(d[dst_len:] == 0xDEADBEEF), "wrote past dst_len"
+    return d[:dst_len]
+
+
+@pytest.mark.parametrize("p,g,log_n,src_len,dst_len", [
+    (GL, 7, 3, 5, 8), (GL, 7, 10, 1, 1024), (GL, 7, 12, 3000, 4000), (GL, 7, 13, 4097, 8191),
+    (GL, 7, 14, 8192, 16383), (GL, 7, 15, 20001, 32768), (GL, 7, 16, 32768, 65535), (GL, 7, 16, 65536, 17),
+    (17, 14, 4, 7, 13), (GL, 49, 14, 5000, 9000),
+])
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_emulated_bounded_out_of_place_transform(emu, p, g, log_n, src_len, dst_len, variant):
+    """poly_mul's transforms: a short operand is zero-extended inside the load phase and the output is clipped
+    inside the store phase (ntt_device_bounded).  Same values as padding / slicing around the plain transform,
+    nothing written past dst_len, the source untouched."""
+    n = 1 << log_n
+    src = oracle.splitmix(p, 900 + log_n, src_len)
+    padded = np.concatenate([src, np.zeros(n - src_len, dtype=np.uint64)])
+    emu.emu_set_variant(variant)   # 0: the kernel's per-mode choice of phase formulation, 1 / 2: force either
+    try:
+        _bounded_checks(emu, p, g, log_n, src, padded, dst_len)
+    finally:
+        emu.emu_set_variant(0)
+
+
+def _bounded_checks(emu, p, g, log_n, src, padded, dst_len):
+    n = 1 << log_n
+    for inverse in (False, True):
+        ref = oracle.ntt_fast(p, padded, inverse=inverse, g=g)
+        keep = src.copy()
+        got = emu_ntt_bounded(emu, p, g, src, dst_len, log_n, inverse=inverse)
+        assert np.array_equal(got, ref[:dst_len]) and np.array_equal(src, keep), (log_n, inverse)
+    if p == GL and g == 7:  # with the fused point-wise multiply (the second transform of poly_mul)
+        mul = oracle.splitmix(p, 77, n)
+        got = emu_ntt_bounded(emu, p, g, src, n, log_n, mul=mul)
+        assert np.array_equal(got, oracle.vec_mul(p, oracle.ntt_fast(p, padded), mul))
