@@ -279,4 +279,46 @@ inline AffinePoint open(const std::vector<PlutoScalarField>& coeffs, PlutoScalar
 }
 }  // namespace kzg
 
+// ---------------------------------------------------------------------------------------------
+// codes::reed_solomon (src/codes/reed_solomon.rs) — §8f "next" row: Message / Codeword over PrimeField<P>
+// ---------------------------------------------------------------------------------------------
+namespace codes {
+
+template <class F>
+struct Coordinate {  // reed_solomon.rs:28-35
+  F x, y;
+  bool operator==(const Coordinate& o) const { return x == o.x && y == o.y; }
+};
+
+template <class F>
+struct Message {  // reed_solomon.rs:13-17
+  std::vector<F> data;
+  explicit Message(std::vector<F> d) : data(std::move(d)) {}
+
+  // encode::<N> (reed_solomon.rs:42-52): (ω_N^i, m(ω_N^i)) for i < N — the transform of the message
+  // zero-padded to N coefficients (ronk_ntt for a power of two, ronk_dft otherwise).
+  std::vector<Coordinate<F>> encode(size_t n) const {
+    if (n < data.size()) throw Panic("Code size must be greater than or equal to K");  // assert_ge, :110-112
+    const F w = F::primitive_root_of_unity(n);                                         // panics if n does not divide P - 1
+    std::vector<F> padded(data);
+    padded.resize(n, F::ZERO());
+    Polynomial<Monomial, F> poly(padded);
+    const auto ys = (n > 1 && (n & (n - 1)) == 0) ? poly.fft().coefficients : poly.dft().coefficients;
+    std::vector<Coordinate<F>> out(n);
+    F x = F::ONE();
+    for (size_t i = 0; i < n; i++, x = x * w) out[i] = {x, ys[i]};
+    return out;
+  }
+  // decode::<M> (reed_solomon.rs:55-107): interpolation through the first K coordinates.
+  static Message decode(const std::vector<Coordinate<F>>& codeword, size_t k) {
+    if (codeword.size() < k) throw Panic("Code size must be greater than or equal to K");
+    std::vector<uint64_t> xs(k), ys(k), out(k);
+    for (size_t i = 0; i < k; i++) { xs[i] = codeword[i].x.value; ys[i] = codeword[i].y.value; }
+    Context::global().check(ronk_poly_interpolate_u64_host(Context::global().get(), F::ORDER, xs.data(), ys.data(), k, out.data()));
+    return Message(Polynomial<Monomial, F>::from_raw(out));
+  }
+};
+
+}  // namespace codes
+
 }  // namespace ronk

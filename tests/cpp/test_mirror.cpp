@@ -75,6 +75,24 @@ int main() {
   CHECK((kzg::commit(vec<S>({7, 16, 1, 11, 1}), srs.first).raw == std::array<uint8_t, 4>{32, 0, 59, 0}));
   CHECK((kzg::open(vec<S>({11, 11, 11, 1}), S(4), srs.first).raw == std::array<uint8_t, 4>{26, 0, 45, 0}));
   CHECK(panics([&] { (void)kzg::commit(std::vector<S>(8, S(1)), srs.first); }));
+  // src/codes/reed_solomon.rs:136-219 (P = 127, K = 3 / 5, N = 3 / 7)
+  using M127 = PrimeField<127>;
+  {
+    codes::Message<M127> msg(vec<M127>({1, 2, 3}));
+    auto cw3 = msg.encode(3);
+    CHECK(cw3.size() == 3 && cw3[1].x == M127(107) && cw3[2].x == M127(19));
+    CHECK(cw3[0].y == M127(6) && cw3[1].y == M127(18) && cw3[2].y == M127(106));
+    CHECK(codes::Message<M127>::decode(msg.encode(7), 3).data == msg.data);
+    codes::Message<M127> msg5(vec<M127>({1, 2, 3, 4, 5}));
+    CHECK(codes::Message<M127>::decode(msg5.encode(7), 5).data == msg5.data);
+    CHECK(panics([&] { (void)msg5.encode(3); }));   // N < K
+    CHECK(panics([&] { (void)msg.encode(4); }));    // 4 does not divide 126
+    using G64 = GoldilocksField;
+    std::vector<G64> big;
+    for (uint64_t i = 0; i < 300; i++) big.emplace_back(i * i + 7);
+    codes::Message<G64> mg(big);
+    CHECK(codes::Message<G64>::decode(mg.encode(512), 300).data == big);   // power of two: the NTT path
+  }
   std::printf(failures ? "%d FAILURES\n" : "cpp mirror ok\n", failures);
   return failures ? 1 : 0;
 }
