@@ -87,8 +87,8 @@ static int build_plan(ronk_ctx* ctx, const F& f, u64 p, u64 g, u32 log_n, NttPla
   return RONK_OK;
 }
 
-template <class F, int MODE, bool INV, int NTHR, int MINB>
-static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A0, u32 tiles, const char* name) {
+template <class F, int MODE, bool INV, int NTHR, int MINB, bool BOUNDED>
+static int launch_tile_nb(ronk_ctx* ctx, const F& f, const NttTileArgs& A0, u32 tiles, const char* name) {
   NttTileArgs A = A0;
   if (MODE == MODE_PASS1) {
     static int pf = -1;  // RONK_PF_DIST: prefetch distance in units of co-resident CTAs (default 1, 0 = off)
@@ -100,13 +100,22 @@ static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A0, u32 t
   }
   const size_t smem = ((size_t)1 << A.tile_log) * sizeof(u64) + (size_t)A.tw_words * sizeof(u64) + 16;
   // set on every launch: the attribute is per device, and several contexts may live in one process
-  RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_tile_kernel<F, MODE, INV, NTHR, MINB>,
+  RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_tile_kernel<F, MODE, INV, NTHR, MINB, BOUNDED>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   {
     LaunchScope ls(ctx, name);
-    ntt_tile_kernel<F, MODE, INV, NTHR, MINB><<<tiles, NTHR, smem, ctx->stream>>>(f, A);
+    ntt_tile_kernel<F, MODE, INV, NTHR, MINB, BOUNDED><<<tiles, NTHR, smem, ctx->stream>>>(f, A);
   }
   return check_launch(ctx, name);
+}
+
+// The bounded instantiation exists only where poly_mul needs it: a zero-padded SOURCE enters through
+// pass 1 / a single-pass tile, a clipped DESTINATION leaves through pass 2 / a single-pass tile.
+template <class F, int MODE, bool INV, int NTHR, int MINB>
+static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
+  const bool bounded = (MODE != MODE_PASS2 && A.src_len != NTT_UNBOUNDED) || (MODE != MODE_PASS1 && A.dst_len != NTT_UNBOUNDED);
+  if (bounded) return launch_tile_nb<F, MODE, INV, NTHR, MINB, true>(ctx, f, A, tiles, name);
+  return launch_tile_nb<F, MODE, INV, NTHR, MINB, false>(ctx, f, A, tiles, name);
 }
 
 template <class F, int MODE, bool INV>

@@ -33,6 +33,8 @@ namespace ronk {
 enum { MODE_SINGLE = 0, MODE_PASS1 = 1, MODE_PASS2 = 2 };
 enum { NTT_FLAG_SCALE = 1, NTT_FLAG_MUL = 2 };
 
+constexpr u64 NTT_UNBOUNDED = ~0ULL;  // NttTileArgs::src_len / dst_len: no bound
+
 struct NttTileArgs {
   const u64* src;
   u64* dst;
@@ -223,14 +225,41 @@ RONK_DEV void ntt_prefetch_pass1(const NttTileArgs& A, u32 tile, u32 tid, u32 nt
   if (col & 3u) return;  // one request per 32-byte sector
   const u32 b = tile / A.tiles_per_batch, sub = tile - b * A.tiles_per_batch;
   const u64* base = A.src + ((u64)b << A.log_n) + ((u64)sub << A.log_c) + ((u64)(tid >> A.log_c) << A.log_n2) + col;
-  for (u32 j = 0; j < per_thread; j++)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((u64)((j << kk) >> A.log_c) << A.log_n2)));
+  const u64* end = A.src + A.src_len;  // a zero-padded operand is shorter than the transform: stay inside it
+  for (u32 j = 0; j < per_thread; j++) {
+    const u64* q = base + ((u64)((j << kk) >> A.log_c) << A.log_n2);
+    if (A.src_len == NTT_UNBOUNDED || q < end) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+  }
 #endif
 }
 
-constexpr u64 NTT_UNBOUNDED = ~0ULL;
+// LD_BATCH loads into registers, then LD_BATCH swizzled stores (see above); BOUNDED adds `index < src_len`.
+template <int MODE, bool BOUNDED>
+RONK_DEV void ntt_load_batches(u64* smem, const NttTileArgs& A, u64 gaddr_t, u32 sw_t, u32 kk, u32 per_thread) {
+  for (u32 j0 = 0; j0 < per_thread; j0 += LD_BATCH) {
+    u64 v[LD_BATCH];
+#pragma unroll
+    for (int i = 0; i < LD_BATCH; i++) {
+      const u32 gj = (j0 + i) << kk;  // warp-uniform
+      if (j0 + i < per_thread) {
+        u64 g;
+        if (MODE == MODE_PASS1) g = gaddr_t + ((u64)(gj >> A.log_c) << A.log_n2);  // kk ≥ log_c: gj has no column bits
+        else g = gaddr_t + gj;
+        bool ok = true;
+        if (MODE == MODE_SINGLE) ok = g < A.total;
+        if (BOUNDED) ok = ok && g < A.src_len;
+        v[i] = ok ? A.src[g] : 0ULL;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LD_BATCH; i++) {
+      const u32 gj = (j0 + i) << kk;
+      if (j0 + i < per_thread) smem[sw_t ^ swz(gj)] = v[i];
+    }
+  }
+}
 
-template <class F, int MODE>
+template <class F, int MODE, bool BOUNDED = false>
 RONK_DEV void ntt_load_phase(u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
   const u32 T = 1u << A.tile_log;
   const u32 kk = ilog2(nthr);
@@ -247,39 +276,7 @@ RONK_DEV void ntt_load_phase(u64* smem, const NttTileArgs& A, u32 tile, u32 tid,
   else gaddr_t = ((u64)b << A.log_n) + ((u64)sub << A.tile_log) + tid;
   const u32 sw_t = swz(tid);
   const u32 per_thread = T >> kk;  // elements per thread (T ≥ nthr)
-  if (A.src_len != NTT_UNBOUNDED) {  // zero-padded operand (batch == 1): same map, bounds-checked loads
-    for (u32 j = 0; j < per_thread; j++) {
-      const u32 gj = j << kk;
-      u64 g;
-      if (MODE == MODE_PASS1) g = gaddr_t + ((u64)(gj >> A.log_c) << A.log_n2);
-      else g = gaddr_t + gj;
-      const bool ok = g < A.src_len && (MODE != MODE_SINGLE || g < A.total);
-      smem[sw_t ^ swz(gj)] = ok ? A.src[g] : 0ULL;
-    }
-    return;
-  }
-  for (u32 j0 = 0; j0 < per_thread; j0 += LD_BATCH) {
-    u64 v[LD_BATCH];
-#pragma unroll
-    for (int i = 0; i < LD_BATCH; i++) {
-      const u32 gj = (j0 + i) << kk;  // warp-uniform
-      if (j0 + i < per_thread) {
-        if (MODE == MODE_SINGLE) {
-          const u64 g = gaddr_t + gj;
-          v[i] = (g < A.total) ? A.src[g] : 0ULL;
-        } else if (MODE == MODE_PASS1) {
-          v[i] = A.src[gaddr_t + ((u64)(gj >> A.log_c) << A.log_n2)];  // kk ≥ log_c: gj has no column bits
-        } else {
-          v[i] = A.src[gaddr_t + gj];
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < LD_BATCH; i++) {
-      const u32 gj = (j0 + i) << kk;
-      if (j0 + i < per_thread) smem[sw_t ^ swz(gj)] = v[i];
-    }
-  }
+  ntt_load_batches<MODE, BOUNDED>(smem, A, gaddr_t, sw_t, kk, per_thread);
 }
 
 // Round schedule: full radix-16 rounds from the top of the NTT index down, then one partial
@@ -335,7 +332,7 @@ RONK_DEV u32 store_perm(const NttTileArgs& A, u32 g) {
   }
 }
 
-template <class F, int MODE, bool INV>
+template <class F, int MODE, bool INV, bool BOUNDED = false>
 RONK_DEV void ntt_store_phase(const F& f, const u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
   const u32 T = 1u << A.tile_log;
   const u32 kk = ilog2(nthr);
@@ -352,7 +349,7 @@ RONK_DEV void ntt_store_phase(const F& f, const u64* smem, const NttTileArgs& A,
     for (u32 j = 0; j < per_thread; j++) {
       const u32 gj = j << kk;
       const u64 ga = base_t + gj;
-      if (ga >= A.total || ga >= A.dst_len) continue;
+      if (ga >= A.total || (BOUNDED && ga >= A.dst_len)) continue;
       u64 v = smem[sw_t ^ swz(store_perm<MODE>(A, gj))];
       if (A.flags & NTT_FLAG_SCALE) v = f.mul_tw(v, A.scale);
       if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[ga]);
@@ -410,7 +407,7 @@ RONK_DEV void ntt_store_phase(const F& f, const u64* smem, const NttTileArgs& A,
     for (u32 j = 0; j < per_thread; j++) {
       const u32 gj = j << kk;  // kk ≥ lc2: gj carries no k1_in bits
       const u64 addr = addr_t + ((u64)(gj >> lc2) << A.log_n1);
-      if (addr >= A.dst_len) continue;
+      if (BOUNDED && addr >= A.dst_len) continue;
       u64 v = smem[sw_t ^ swz(store_perm<MODE>(A, gj))];
       if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[addr]);
       A.dst[addr] = v;
@@ -419,7 +416,7 @@ RONK_DEV void ntt_store_phase(const F& f, const u64* smem, const NttTileArgs& A,
 }
 
 // ---- previous formulation of the phases (index math per element), kept selectable per mode ----
-template <class F, int MODE>
+template <class F, int MODE, bool BOUNDED = false>
 RONK_DEV void ntt_load_phase_v0(u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
   const u32 T = 1u << A.tile_log;
   u32 b = 0, sub = tile;
@@ -440,11 +437,11 @@ RONK_DEV void ntt_load_phase_v0(u64* smem, const NttTileArgs& A, u32 tile, u32 t
       const u32 e = e0 + i * nthr;
       if (MODE == MODE_SINGLE) {
         const u64 g = base + e;
-        v[i] = (e < T && g < A.total && g < A.src_len) ? A.src[g] : 0ULL;
+        v[i] = (e < T && g < A.total && (!BOUNDED || g < A.src_len)) ? A.src[g] : 0ULL;
       } else if (MODE == MODE_PASS1) {
         const u32 j1 = e >> A.log_c, c = e & cmask;
         const u64 g = base + ((u64)j1 << A.log_n2) + c;
-        v[i] = (e < T && g < A.src_len) ? A.src[g] : 0ULL;
+        v[i] = (e < T && (!BOUNDED || g < A.src_len)) ? A.src[g] : 0ULL;
       } else {
         v[i] = (e < T) ? A.src[base + e] : 0ULL;
       }
@@ -457,7 +454,7 @@ RONK_DEV void ntt_load_phase_v0(u64* smem, const NttTileArgs& A, u32 tile, u32 t
   }
 }
 
-template <class F, int MODE, bool INV>
+template <class F, int MODE, bool INV, bool BOUNDED = false>
 RONK_DEV void ntt_store_phase_v0(const F& f, const u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
   const u32 T = 1u << A.tile_log;
   const u32 M = 1u << A.log_m;
@@ -469,7 +466,7 @@ RONK_DEV void ntt_store_phase_v0(const F& f, const u64* smem, const NttTileArgs&
   if (MODE == MODE_SINGLE) {
     const u64 base = (u64)tile << A.tile_log;
     for (u32 g = tid; g < T; g += nthr) {
-      if (base + g >= A.total || base + g >= A.dst_len) continue;
+      if (base + g >= A.total || (BOUNDED && base + g >= A.dst_len)) continue;
       const u32 bt = g >> A.log_m, k = g & (M - 1u);
       const u32 e = (bt << A.log_m) | bitrev(k, A.log_m);
       u64 v = smem[swz(e)];
@@ -499,21 +496,11 @@ RONK_DEV void ntt_store_phase_v0(const F& f, const u64* smem, const NttTileArgs&
   } else {
     const u32 lc2 = A.log_c;  // pass-2 tile: columns are the C2 adjacent k1 values
     const u64 base = ((u64)b << A.log_n) + ((u64)sub << lc2);
-    if (A.dst_len != NTT_UNBOUNDED) {  // clipped output (batch == 1); the unbounded loop below stays as it was
-      for (u32 g = tid; g < T; g += nthr) {
-        const u32 k2 = g >> lc2, k1_in = g & ((1u << lc2) - 1u);
-        const u64 addr = base + k1_in + ((u64)k2 << A.log_n1);
-        if (addr >= A.dst_len) continue;
-        u64 v = smem[swz((bitrev(k2, A.log_m) << lc2) | k1_in)];
-        if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[addr]);
-        A.dst[addr] = v;
-      }
-      return;
-    }
     for (u32 g = tid; g < T; g += nthr) {
       const u32 k2 = g >> lc2, k1_in = g & ((1u << lc2) - 1u);
       const u32 e = (bitrev(k2, A.log_m) << lc2) | k1_in;
       const u64 addr = base + k1_in + ((u64)k2 << A.log_n1);
+      if (BOUNDED && addr >= A.dst_len) continue;
       u64 v = smem[swz(e)];
       if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[addr]);
       A.dst[addr] = v;
@@ -731,7 +718,8 @@ __global__ void __launch_bounds__(NTHR, 1) ntt_pipe_kernel(const F f, const NttT
 }
 
 // Shared memory: [ tile: T·8 B | twiddles: M·8 B | mbarrier: 8 B ]
-template <class F, int MODE, bool INV, int NTHR, int MINB>
+// BOUNDED instantiations (poly_mul only) honour A.src_len / A.dst_len; the unbounded ones carry no such code.
+template <class F, int MODE, bool INV, int NTHR, int MINB, bool BOUNDED = false>
 __global__ void __launch_bounds__(NTHR, MINB) ntt_tile_kernel(const F f, const NttTileArgs A) {
   extern __shared__ __align__(128) u64 smem[];
   const u32 tid = threadIdx.x, tile = blockIdx.x;
@@ -745,8 +733,8 @@ __global__ void __launch_bounds__(NTHR, MINB) ntt_tile_kernel(const F f, const N
     mbar_expect_tx(bar, A.tw_words * 8u);
     tma_bulk_g2s(tw, A.tw_tile, A.tw_words * 8u, bar);  // lands while the tile itself is being loaded
   }
-  if ((RONK_LOAD_V0_MASK >> MODE) & 1) ntt_load_phase_v0<F, MODE>(smem, A, tile, tid, NTHR);
-  else ntt_load_phase<F, MODE>(smem, A, tile, tid, NTHR);
+  if ((RONK_LOAD_V0_MASK >> MODE) & 1) ntt_load_phase_v0<F, MODE, BOUNDED>(smem, A, tile, tid, NTHR);
+  else ntt_load_phase<F, MODE, BOUNDED>(smem, A, tile, tid, NTHR);
   if (MODE == MODE_PASS1 && A.prefetch_dist && tile + A.prefetch_dist < gridDim.x)
     ntt_prefetch_pass1(A, tile + A.prefetch_dist, tid, NTHR);
   __syncthreads();
@@ -756,8 +744,8 @@ __global__ void __launch_bounds__(NTHR, MINB) ntt_tile_kernel(const F f, const N
     ntt_round_dispatch<F, INV>(f, smem, tw, A, nst, wb, lcur, tid, NTHR);
     __syncthreads();
   }
-  if ((RONK_STORE_V0_MASK >> MODE) & 1) ntt_store_phase_v0<F, MODE, INV>(f, smem, A, tile, tid, NTHR);
-  else ntt_store_phase<F, MODE, INV>(f, smem, A, tile, tid, NTHR);
+  if ((RONK_STORE_V0_MASK >> MODE) & 1) ntt_store_phase_v0<F, MODE, INV, BOUNDED>(f, smem, A, tile, tid, NTHR);
+  else ntt_store_phase<F, MODE, INV, BOUNDED>(f, smem, A, tile, tid, NTHR);
 }
 
 // 2-D per-round twiddle table from the 1-D table ω_M^e (both in twiddle form); pads = 0

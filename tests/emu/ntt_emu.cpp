@@ -64,26 +64,34 @@ std::vector<u64> table2d(const std::vector<u64>& tw1d, u32 log_m, bool inverse) 
 int g_variant = 0;
 bool use_v0(int mask, int mode) { return g_variant == 0 ? ((mask >> mode) & 1) != 0 : g_variant == 2; }
 
-template <class F, int MODE, bool INV>
-void run_tiles(const F& f, const NttTileArgs& A, u64 tiles) {
+template <class F, int MODE, bool INV, bool BOUNDED>
+void run_tiles_b(const F& f, const NttTileArgs& A, u64 tiles) {
   const u32 T = 1u << A.tile_log, nthr = (T / 32 >= 32) ? T / 32 : 32;
   std::vector<u64> smem(T);
   for (u64 tile = 0; tile < tiles; tile++) {
     for (u32 t = 0; t < nthr; t++) {
-      if (use_v0(RONK_LOAD_V0_MASK, MODE)) ntt_load_phase_v0<F, MODE>(smem.data(), A, (u32)tile, t, nthr);
-      else ntt_load_phase<F, MODE>(smem.data(), A, (u32)tile, t, nthr);
+      if (use_v0(RONK_LOAD_V0_MASK, MODE)) ntt_load_phase_v0<F, MODE, BOUNDED>(smem.data(), A, (u32)tile, t, nthr);
+      else ntt_load_phase<F, MODE, BOUNDED>(smem.data(), A, (u32)tile, t, nthr);
     }
     u32 nst, wb, lcur;
     for (u32 r = 0; ntt_round_plan(A, r, &nst, &wb, &lcur); r++)
       for (u32 t = 0; t < nthr; t++) ntt_round_dispatch<F, INV>(f, smem.data(), A.tw_tile, A, nst, wb, lcur, t, nthr);
     for (u32 t = 0; t < nthr; t++) {
-      if (use_v0(RONK_STORE_V0_MASK, MODE)) ntt_store_phase_v0<F, MODE, INV>(f, smem.data(), A, (u32)tile, t, nthr);
-      else ntt_store_phase<F, MODE, INV>(f, smem.data(), A, (u32)tile, t, nthr);
+      if (use_v0(RONK_STORE_V0_MASK, MODE)) ntt_store_phase_v0<F, MODE, INV, BOUNDED>(f, smem.data(), A, (u32)tile, t, nthr);
+      else ntt_store_phase<F, MODE, INV, BOUNDED>(f, smem.data(), A, (u32)tile, t, nthr);
     }
   }
 }
 
 // src == nullptr: in place; otherwise the bounded out-of-place form of run_ntt() in ntt.cu (batch 1)
+// same choice of instantiation as launch_tile_n() in ntt.cu
+template <class F, int MODE, bool INV>
+void run_tiles(const F& f, const NttTileArgs& A, u64 tiles) {
+  const bool bounded = (MODE != MODE_PASS2 && A.src_len != NTT_UNBOUNDED) || (MODE != MODE_PASS1 && A.dst_len != NTT_UNBOUNDED);
+  if (bounded) run_tiles_b<F, MODE, INV, true>(f, A, tiles);
+  else run_tiles_b<F, MODE, INV, false>(f, A, tiles);
+}
+
 template <class F, bool INV>
 int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 log_n, u32 batch, u32 tile_cap,
         u32 pref1, u32 pref2, const u64* src = nullptr, u64 src_len = NTT_UNBOUNDED, u64 dst_len = NTT_UNBOUNDED) {
