@@ -87,7 +87,7 @@ static int build_plan(ronk_ctx* ctx, const F& f, u64 p, u64 g, u32 log_n, NttPla
   return RONK_OK;
 }
 
-template <class F, int MODE, bool INV, int NTHR, int MINB, bool BOUNDED>
+template <class F, int MODE, bool INV, int NTHR, int MINB, bool BOUNDED, bool FMUL>
 static int launch_tile_nb(ronk_ctx* ctx, const F& f, const NttTileArgs& A0, u32 tiles, const char* name) {
   NttTileArgs A = A0;
   if (MODE == MODE_PASS1) {
@@ -100,11 +100,11 @@ static int launch_tile_nb(ronk_ctx* ctx, const F& f, const NttTileArgs& A0, u32 
   }
   const size_t smem = ((size_t)1 << A.tile_log) * sizeof(u64) + (size_t)A.tw_words * sizeof(u64) + 16;
   // set on every launch: the attribute is per device, and several contexts may live in one process
-  RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_tile_kernel<F, MODE, INV, NTHR, MINB, BOUNDED>,
+  RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_tile_kernel<F, MODE, INV, NTHR, MINB, BOUNDED, FMUL>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   {
     LaunchScope ls(ctx, name);
-    ntt_tile_kernel<F, MODE, INV, NTHR, MINB, BOUNDED><<<tiles, NTHR, smem, ctx->stream>>>(f, A);
+    ntt_tile_kernel<F, MODE, INV, NTHR, MINB, BOUNDED, FMUL><<<tiles, NTHR, smem, ctx->stream>>>(f, A);
   }
   return check_launch(ctx, name);
 }
@@ -114,8 +114,15 @@ static int launch_tile_nb(ronk_ctx* ctx, const F& f, const NttTileArgs& A0, u32 
 template <class F, int MODE, bool INV, int NTHR, int MINB>
 static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
   const bool bounded = (MODE != MODE_PASS2 && A.src_len != NTT_UNBOUNDED) || (MODE != MODE_PASS1 && A.dst_len != NTT_UNBOUNDED);
-  if (bounded) return launch_tile_nb<F, MODE, INV, NTHR, MINB, true>(ctx, f, A, tiles, name);
-  return launch_tile_nb<F, MODE, INV, NTHR, MINB, false>(ctx, f, A, tiles, name);
+  // the fused point-wise multiply of pass 2 (forward transforms of poly_mul) has its own instantiation too
+  constexpr bool can_fmul = MODE == MODE_PASS2 && !INV && ((RONK_STORE_V0_MASK >> MODE_PASS2) & 1);
+  const bool fmul = can_fmul && (A.flags & NTT_FLAG_MUL);
+  if (can_fmul && fmul) {
+    if (bounded) return launch_tile_nb<F, MODE, INV, NTHR, MINB, true, can_fmul>(ctx, f, A, tiles, name);
+    return launch_tile_nb<F, MODE, INV, NTHR, MINB, false, can_fmul>(ctx, f, A, tiles, name);
+  }
+  if (bounded) return launch_tile_nb<F, MODE, INV, NTHR, MINB, true, false>(ctx, f, A, tiles, name);
+  return launch_tile_nb<F, MODE, INV, NTHR, MINB, false, false>(ctx, f, A, tiles, name);
 }
 
 template <class F, int MODE, bool INV>

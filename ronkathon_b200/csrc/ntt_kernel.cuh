@@ -454,7 +454,10 @@ RONK_DEV void ntt_load_phase_v0(u64* smem, const NttTileArgs& A, u32 tile, u32 t
   }
 }
 
-template <class F, int MODE, bool INV, bool BOUNDED = false>
+// FMUL (pass 2 only): the caller guarantees NTT_FLAG_MUL; the point-wise operand is then fetched in batches
+// ahead of the stores — in the plain loop every mul_src load sits behind the previous store (the two arrays
+// may alias as far as the compiler knows) and pays a full memory latency per element.
+template <class F, int MODE, bool INV, bool BOUNDED = false, bool FMUL = false>
 RONK_DEV void ntt_store_phase_v0(const F& f, const u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
   const u32 T = 1u << A.tile_log;
   const u32 M = 1u << A.log_m;
@@ -496,14 +499,36 @@ RONK_DEV void ntt_store_phase_v0(const F& f, const u64* smem, const NttTileArgs&
   } else {
     const u32 lc2 = A.log_c;  // pass-2 tile: columns are the C2 adjacent k1 values
     const u64 base = ((u64)b << A.log_n) + ((u64)sub << lc2);
-    for (u32 g = tid; g < T; g += nthr) {
-      const u32 k2 = g >> lc2, k1_in = g & ((1u << lc2) - 1u);
-      const u32 e = (bitrev(k2, A.log_m) << lc2) | k1_in;
-      const u64 addr = base + k1_in + ((u64)k2 << A.log_n1);
-      if (BOUNDED && addr >= A.dst_len) continue;
-      u64 v = smem[swz(e)];
-      if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[addr]);
-      A.dst[addr] = v;
+    if (FMUL) {
+      constexpr int SB = 8;
+      for (u32 g0 = tid; g0 < T; g0 += nthr * SB) {
+        u64 m[SB];
+#pragma unroll
+        for (int i = 0; i < SB; i++) {
+          const u32 g = g0 + i * nthr;
+          const u64 addr = base + (g & ((1u << lc2) - 1u)) + ((u64)(g >> lc2) << A.log_n1);
+          m[i] = (g < T && !(BOUNDED && addr >= A.dst_len)) ? A.mul_src[addr] : 0ULL;
+        }
+#pragma unroll
+        for (int i = 0; i < SB; i++) {
+          const u32 g = g0 + i * nthr;
+          if (g >= T) continue;
+          const u32 k2 = g >> lc2, k1_in = g & ((1u << lc2) - 1u);
+          const u64 addr = base + k1_in + ((u64)k2 << A.log_n1);
+          if (BOUNDED && addr >= A.dst_len) continue;
+          A.dst[addr] = f.mul(smem[swz((bitrev(k2, A.log_m) << lc2) | k1_in)], m[i]);
+        }
+      }
+    } else {
+      for (u32 g = tid; g < T; g += nthr) {
+        const u32 k2 = g >> lc2, k1_in = g & ((1u << lc2) - 1u);
+        const u32 e = (bitrev(k2, A.log_m) << lc2) | k1_in;
+        const u64 addr = base + k1_in + ((u64)k2 << A.log_n1);
+        if (BOUNDED && addr >= A.dst_len) continue;
+        u64 v = smem[swz(e)];
+        if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[addr]);
+        A.dst[addr] = v;
+      }
     }
   }
 }
@@ -719,7 +744,7 @@ __global__ void __launch_bounds__(NTHR, 1) ntt_pipe_kernel(const F f, const NttT
 
 // Shared memory: [ tile: T·8 B | twiddles: M·8 B | mbarrier: 8 B ]
 // BOUNDED instantiations (poly_mul only) honour A.src_len / A.dst_len; the unbounded ones carry no such code.
-template <class F, int MODE, bool INV, int NTHR, int MINB, bool BOUNDED = false>
+template <class F, int MODE, bool INV, int NTHR, int MINB, bool BOUNDED = false, bool FMUL = false>
 __global__ void __launch_bounds__(NTHR, MINB) ntt_tile_kernel(const F f, const NttTileArgs A) {
   extern __shared__ __align__(128) u64 smem[];
   const u32 tid = threadIdx.x, tile = blockIdx.x;
@@ -744,7 +769,7 @@ __global__ void __launch_bounds__(NTHR, MINB) ntt_tile_kernel(const F f, const N
     ntt_round_dispatch<F, INV>(f, smem, tw, A, nst, wb, lcur, tid, NTHR);
     __syncthreads();
   }
-  if ((RONK_STORE_V0_MASK >> MODE) & 1) ntt_store_phase_v0<F, MODE, INV, BOUNDED>(f, smem, A, tile, tid, NTHR);
+  if ((RONK_STORE_V0_MASK >> MODE) & 1) ntt_store_phase_v0<F, MODE, INV, BOUNDED, FMUL>(f, smem, A, tile, tid, NTHR);
   else ntt_store_phase<F, MODE, INV, BOUNDED>(f, smem, A, tile, tid, NTHR);
 }
 

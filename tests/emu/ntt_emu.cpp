@@ -64,7 +64,7 @@ std::vector<u64> table2d(const std::vector<u64>& tw1d, u32 log_m, bool inverse) 
 int g_variant = 0;
 bool use_v0(int mask, int mode) { return g_variant == 0 ? ((mask >> mode) & 1) != 0 : g_variant == 2; }
 
-template <class F, int MODE, bool INV, bool BOUNDED>
+template <class F, int MODE, bool INV, bool BOUNDED, bool FMUL = false>
 void run_tiles_b(const F& f, const NttTileArgs& A, u64 tiles) {
   const u32 T = 1u << A.tile_log, nthr = (T / 32 >= 32) ? T / 32 : 32;
   std::vector<u64> smem(T);
@@ -77,7 +77,7 @@ void run_tiles_b(const F& f, const NttTileArgs& A, u64 tiles) {
     for (u32 r = 0; ntt_round_plan(A, r, &nst, &wb, &lcur); r++)
       for (u32 t = 0; t < nthr; t++) ntt_round_dispatch<F, INV>(f, smem.data(), A.tw_tile, A, nst, wb, lcur, t, nthr);
     for (u32 t = 0; t < nthr; t++) {
-      if (use_v0(RONK_STORE_V0_MASK, MODE)) ntt_store_phase_v0<F, MODE, INV, BOUNDED>(f, smem.data(), A, (u32)tile, t, nthr);
+      if (use_v0(RONK_STORE_V0_MASK, MODE)) ntt_store_phase_v0<F, MODE, INV, BOUNDED, FMUL>(f, smem.data(), A, (u32)tile, t, nthr);
       else ntt_store_phase<F, MODE, INV, BOUNDED>(f, smem.data(), A, (u32)tile, t, nthr);
     }
   }
@@ -88,6 +88,12 @@ void run_tiles_b(const F& f, const NttTileArgs& A, u64 tiles) {
 template <class F, int MODE, bool INV>
 void run_tiles(const F& f, const NttTileArgs& A, u64 tiles) {
   const bool bounded = (MODE != MODE_PASS2 && A.src_len != NTT_UNBOUNDED) || (MODE != MODE_PASS1 && A.dst_len != NTT_UNBOUNDED);
+  constexpr bool can_fmul = MODE == MODE_PASS2 && !INV;
+  if (can_fmul && (A.flags & NTT_FLAG_MUL)) {
+    if (bounded) run_tiles_b<F, MODE, INV, true, can_fmul>(f, A, tiles);
+    else run_tiles_b<F, MODE, INV, false, can_fmul>(f, A, tiles);
+    return;
+  }
   if (bounded) run_tiles_b<F, MODE, INV, true>(f, A, tiles);
   else run_tiles_b<F, MODE, INV, false>(f, A, tiles);
 }
