@@ -186,15 +186,27 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
   }
   const size_t bytes = ((size_t)batch << log_n) * sizeof(u64);
   RONK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, bytes));
-  static int pref1 = 0, pref2 = 0;  // preferred tile sizes (log2); RONK_TILE1 / RONK_TILE2 for experiments
+  static int pref1 = 0, pref2 = 0, adapt = 1;  // preferred tile sizes (log2); RONK_TILE1 / RONK_TILE2 for experiments
   if (!pref1) {
     const char* s1 = getenv("RONK_TILE1");
     const char* s2 = getenv("RONK_TILE2");
+    const char* s3 = getenv("RONK_TILE_ADAPT");
     pref1 = s1 ? atoi(s1) : 14;  // measured best on B200: strided pass-1 reads want 32-byte segments
     pref2 = s2 ? atoi(s2) : 13;
+    adapt = s3 ? atoi(s3) : 1;
+  }
+  // The preferred sizes are tuned for grids of ≥ 1000 tiles.  A mid-size job (one 2^20 transform is 64 tiles of
+  // 2^14) would leave most SMs idle, so shrink the tiles until the grid fills the GPU, but never below 4 columns
+  // in pass 1 (32-byte segments) / 2 in pass 2.
+  u32 p1 = (u32)pref1, p2 = (u32)pref2;
+  if (adapt) {
+    const u64 total = (u64)batch << log_n;
+    const u64 want = 2ull * (u64)ctx->sm_count;
+    while (p1 > pl.log_n1 + 2 && p1 > 11 && (total >> p1) < want) p1--;
+    while (p2 > pl.log_n2 + 1 && p2 > 11 && (total >> p2) < 2 * want) p2--;
   }
   u32 tile1, tile2;
-  ntt_pass_tiles(log_n, (u32)pref1, (u32)pref2, &tile1, &tile2);
+  ntt_pass_tiles(log_n, p1, p2, &tile1, &tile2);
   // pass 1: N1-point transforms down the columns, inter-pass twiddle, blocked write to the workspace
   NttTileArgs A1 = ntt_args_pass1(src, (u64*)ctx->ws, pl.tw1_2d[INV ? 1 : 0], pl.tw_lo, INV ? pl.tw_hi_inv : pl.tw2, pl.tw2,
                                   log_n, batch, tile1, tile2, &tiles);

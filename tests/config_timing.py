@@ -91,6 +91,13 @@ def main():
                                      "field_muls_per_s": bt * (1 << 15) * 16 / (ms * 1e-3),
                                      "kernel_ms": kernels(ctx, lambda: ops.ntt_(ctx, d, 16, batch=bt))}
     del d
+    # single transforms of every two-pass size (ms), to see the mid-size regime
+    sweep = {}
+    for lg in range(14, 25):
+        dd = ops.splitmix_fill(ctx, 1 << lg, 42)
+        sweep[f"2^{lg}"] = round(timed(lambda: ops.ntt_(ctx, dd, lg)), 4)
+        del dd
+    out["single_transform_ms"] = sweep
     for log_n in (10, 16, 20, 24):
         n = 1 << log_n
         pts, sc = msm_inputs(n)

@@ -128,13 +128,21 @@ def test_emulated_goldilocks_single_pass(emu, log_n, mont):
     assert np.array_equal(emu_ntt(emu, p, g, X, log_n, batch, inverse=True), a)
 
 
+def test_emulated_adaptive_tiles_config2(emu):
+    """The tile shapes run_ntt() picks for one 2^20 transform (config 2) on a 148-SM GPU: 2^12 / 2^11."""
+    a = oracle.splitmix(GL, 42, 1 << 20)
+    X = emu_ntt(emu, GL, 7, a, 20, tiles=(12, 11))
+    assert np.array_equal(X, oracle.ntt_fast(GL, a))
+    assert np.array_equal(emu_ntt(emu, GL, 7, X, 20, inverse=True, tiles=(12, 11)), a)
+
+
 def test_emulated_golden_vectors(emu, gold64):
     assert list(emu_ntt(emu, GL, 7, list(range(1, 9)), 3)) == gold64["ntt8_1to8"]
     a = oracle.splitmix(GL, 42, 1024)
     assert list(emu_ntt(emu, GL, 7, a, 10)) == gold64["ntt_2_10_full"]
 
 
-@pytest.mark.parametrize("tiles", [(13, 13), (14, 14), (13, 14), (14, 13), (12, 12)])
+@pytest.mark.parametrize("tiles", [(13, 13), (14, 14), (13, 14), (14, 13), (12, 12), (12, 11), (13, 12), (11, 11)])
 @pytest.mark.parametrize("log_n,batch", [(14, 2), (15, 1), (16, 2), (17, 1), (18, 1)])
 def test_emulated_goldilocks_two_pass(emu, log_n, batch, tiles):
     n = 1 << log_n
