@@ -73,3 +73,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "ronk_oracle" not in text, f
+
+
+def test_rust_sys_crate_declares_every_header_symbol():
+    """bindings/rust is shipped as source only (no rustc in the build image), so at least keep its extern block
+    in step with include/ronk_b200.h: every exported function must be declared there."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "ronk_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(ronk_[a-z0-9_]+)\s*\(", header)))
+    rs = open(os.path.join(root, "bindings", "rust", "ronkathon-b200-sys", "src", "lib.rs")).read()
+    missing = [n for n in names if not re.search(r"\bfn\s+" + n + r"\s*\(", rs)]
+    assert not missing, missing
