@@ -125,37 +125,12 @@ static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 ti
   return launch_tile_nb<F, MODE, INV, NTHR, MINB, false, false>(ctx, f, A, tiles, name);
 }
 
-template <class F, int MODE, bool INV>
-static int launch_pipe(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
-  const size_t smem = ((size_t)2 << A.tile_log) * sizeof(u64) + (size_t)A.tw_words * sizeof(u64) + 16;
-  RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_pipe_kernel<F, MODE, INV, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      226 * 1024));
-  const u32 grid = tiles < (u32)ctx->sm_count ? tiles : (u32)ctx->sm_count;
-  {
-    LaunchScope ls(ctx, name);
-    ntt_pipe_kernel<F, MODE, INV, 512><<<grid, 512, smem, ctx->stream>>>(f, A, tiles);
-  }
-  return check_launch(ctx, name);
-}
-
 // CTA shape: every thread owns 32 tile elements per round (two radix-16 groups, ≤128 registers, no
 // spills).  A 2^14 tile is one 512-thread CTA per SM; a 2^13 tile is a 256-thread CTA and two of
 // them share an SM, so one CTA's load/store phases overlap the other's butterflies.
 template <class F, int MODE, bool INV>
 static int launch_tile(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
   const u32 groups = (1u << A.tile_log) / 16;
-  // RONK_NTT_PIPE=1 selects the persistent cp.async double-buffered kernel.  Measured on B200 it is
-  // SLOWER (pass 2: 0.246 ms vs 0.213 ms): the transform is ALU-pipe-bound, not latency-bound, and one
-  // radix-16 group per thread has less ILP than two.  Kept for experiments; off by default.
-  static int pipe = -1;
-  if (pipe < 0) {
-    const char* s = getenv("RONK_NTT_PIPE");
-    pipe = s ? atoi(s) : 0;
-  }
-  // 2^13-element tiles with enough of them to keep every SM busy: persistent + cp.async double buffering
-  if (pipe && A.tile_log == 13 && A.log_m <= 13 && tiles >= 2u * (u32)ctx->sm_count &&
-      ((size_t)2 << 13) * 8 + (size_t)A.tw_words * 8 + 16 <= 226 * 1024)
-    return launch_pipe<F, MODE, INV>(ctx, f, A, tiles, name);
   if (groups >= 1024) return launch_tile_n<F, MODE, INV, 512, 1>(ctx, f, A, tiles, name);
   if (groups >= 512) return launch_tile_n<F, MODE, INV, 256, 2>(ctx, f, A, tiles, name);
   if (groups >= 128) return launch_tile_n<F, MODE, INV, 128, 2>(ctx, f, A, tiles, name);

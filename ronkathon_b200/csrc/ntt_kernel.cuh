@@ -658,90 +658,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
                : "memory");
 }
 
-// --- asynchronous element copies (LDGSTS) for the double-buffered persistent kernel --------------
-__device__ __forceinline__ void cp_async8(u64* smem_dst, const u64* gsrc, u32 src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((u32)__cvta_generic_to_shared(smem_dst)),
-               "l"(gsrc), "r"(src_bytes)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// Same index map as ntt_load_phase, but the elements travel HBM → shared memory asynchronously
-// (no registers, no stall): issued one tile ahead of the butterflies that consume them.
-template <class F, int MODE>
-__device__ __forceinline__ void ntt_load_async(u64* smem, const NttTileArgs& A, u32 tile, u32 tid, u32 nthr) {
-  const u32 T = 1u << A.tile_log;
-  u32 b = 0, sub = tile;
-  if (MODE != MODE_SINGLE) {
-    b = tile / A.tiles_per_batch;
-    sub = tile - b * A.tiles_per_batch;
-  }
-  u64 base;
-  if (MODE == MODE_SINGLE) base = (u64)tile << A.tile_log;
-  else if (MODE == MODE_PASS1) base = ((u64)b << A.log_n) + ((u64)sub << A.log_c);
-  else base = ((u64)b << A.log_n) + ((u64)sub << A.tile_log);
-  const u32 cmask = (1u << A.log_c) - 1u;
-#pragma unroll 4
-  for (u32 e = tid; e < T; e += nthr) {
-    if (MODE == MODE_SINGLE) {
-      const u64 g = base + e;
-      const bool ok = g < A.total;
-      cp_async8(smem + swz(e), A.src + (ok ? g : 0), ok ? 8u : 0u);  // zero-fill past the end
-    } else if (MODE == MODE_PASS1) {
-      const u32 j1 = e >> A.log_c, c = e & cmask;
-      cp_async8(smem + swz(e), A.src + base + ((u64)j1 << A.log_n2) + c, 8u);
-    } else {
-      cp_async8(smem + swz(e), A.src + base + e, 8u);
-    }
-  }
-}
-
-// Persistent, double-buffered variant: one CTA per SM walks tiles blockIdx.x, +gridDim.x, …;
-// while the rounds of tile i run out of one buffer, tile i+1 streams into the other.
-// Shared memory: [ buffer 0: T·8 B | buffer 1: T·8 B | twiddles: M·8 B | mbarrier ]
-template <class F, int MODE, bool INV, int NTHR>
-__global__ void __launch_bounds__(NTHR, 1) ntt_pipe_kernel(const F f, const NttTileArgs A, const u32 tiles) {
-  extern __shared__ __align__(128) u64 smem[];
-  const u32 tid = threadIdx.x;
-  const u32 T = 1u << A.tile_log;
-  u64* buf0 = smem;
-  u64* buf1 = smem + T;
-  u64* tw = smem + 2 * T;
-  u64* bar = tw + A.tw_words;
-  const bool use_tw = A.log_m > 4;
-  u32 t = blockIdx.x;
-  if (t >= tiles) return;
-  if (use_tw && tid == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar, A.tw_words * 8u);
-    tma_bulk_g2s(tw, A.tw_tile, A.tw_words * 8u, bar);
-  }
-  ntt_load_async<F, MODE>(buf0, A, t, tid, NTHR);
-  cp_async_commit();
-  for (u32 i = 0; t < tiles; i++, t += gridDim.x) {
-    u64* cur = (i & 1) ? buf1 : buf0;
-    u64* nxt = (i & 1) ? buf0 : buf1;
-    const u32 tn = t + gridDim.x;
-    if (tn < tiles) ntt_load_async<F, MODE>(nxt, A, tn, tid, NTHR);
-    cp_async_commit();
-    cp_async_wait<1>();  // everything but the group just committed has landed → tile t is in `cur`
-    __syncthreads();
-    if (i == 0 && use_tw) mbar_wait(bar, 0);
-    u32 nst, wb, lcur;
-    for (u32 r = 0; ntt_round_plan(A, r, &nst, &wb, &lcur); r++) {
-      ntt_round_dispatch<F, INV>(f, cur, tw, A, nst, wb, lcur, tid, NTHR);
-      __syncthreads();
-    }
-    ntt_store_phase<F, MODE, INV>(f, cur, A, t, tid, NTHR);
-    __syncthreads();  // `cur` is the prefetch target of the next iteration
-  }
-}
-
 // Shared memory: [ tile: T·8 B | twiddles: M·8 B | mbarrier: 8 B ]
 // BOUNDED instantiations (poly_mul only) honour A.src_len / A.dst_len; the unbounded ones carry no such code.
 template <class F, int MODE, bool INV, int NTHR, int MINB, bool BOUNDED = false, bool FMUL = false>
