@@ -145,9 +145,14 @@ __global__ void __launch_bounds__(MSM_THREADS) msm_bucket_kernel(const u32* __re
   __syncthreads();
   const size_t stride = (size_t)gridDim.x * MSM_THREADS;
   bool bad = false;
-  for (size_t i = (size_t)blockIdx.x * MSM_THREADS + t; i < n; i += stride) {
-    const u32 w = points[i];
-    const u32 s = scalars[i];
+  // the loads of the next pair are issued before the current one is processed: the add chain below is
+  // latency-bound (profiles/r01l_msm_bucket_2_10_metrics.txt) and would otherwise wait a full memory
+  // latency per term
+  size_t i = (size_t)blockIdx.x * MSM_THREADS + t;
+  u32 w_next = (i < n) ? points[i] : PT_INF, s_next = (i < n) ? scalars[i] : 0u;
+  for (; i < n; i += stride) {
+    const u32 w = w_next, s = s_next;
+    if (i + stride < n) { w_next = points[i + stride]; s_next = scalars[i + stride]; }
     if (s >= 17 || !pt_valid(w)) { bad = true; continue; }
     if (s == 0 || w == PT_INF) continue;  // g1 * 0 = Infinity (curve/mod.rs:163-165)
     bucket[s - 1][t] = pt_add_t(bucket[s - 1][t], w, inv);
