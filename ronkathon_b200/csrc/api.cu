@@ -36,7 +36,7 @@ int ronk_ctx_create(ronk_ctx** out, int device, void* stream) {
     return RONK_EUNSUPPORTED;
   }
   if (cudaMalloc((void**)&ctx->d_flag, sizeof(int)) != cudaSuccess ||
-      cudaMallocHost((void**)&ctx->h_flag, sizeof(int)) != cudaSuccess) {
+      cudaMallocHost((void**)&ctx->h_flag, 32 * sizeof(int)) != cudaSuccess) {  // h_flag[0] + 31 words of small results
     delete ctx;
     return RONK_ENOMEM;
   }

@@ -202,9 +202,10 @@ RONK_DEV void ntt_round(const F& f, u64* smem, const u64* tw, const NttTileArgs&
 #ifndef RONK_LD_BATCH
 #define RONK_LD_BATCH 8
 #endif
-constexpr int LD_BATCH = RONK_LD_BATCH;
+constexpr int LD_BATCH = RONK_LD_BATCH;  // strided pass-1 columns: 8 (deeper was slower when the tile came from HBM)
+// contiguous pass-2 / single tiles: a thread's whole share (32 elements) in flight — 16 → 0.1704 ms, 32 → 0.1685 ms
 #ifndef RONK_LD_BATCH_CONTIG
-#define RONK_LD_BATCH_CONTIG 16
+#define RONK_LD_BATCH_CONTIG 32
 #endif
 RONK_DEV u32 ilog2(u32 v) {
   u32 l = 0;

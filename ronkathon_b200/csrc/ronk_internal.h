@@ -57,7 +57,7 @@ struct ronk_ctx {
   cudaEvent_t ev_h2d[kSlots] = {}, ev_compute[kSlots] = {}, ev_d2h[kSlots] = {};
   bool slot_pending[kSlots] = {};
   int* d_flag = nullptr;  // device error flag
-  int* h_flag = nullptr;  // pinned host mirror
+  int* h_flag = nullptr;  // pinned host mirror: h_flag[0] = error flag, h_flag[1..31] = small results (msm.cu)
 };
 
 namespace ronk {
