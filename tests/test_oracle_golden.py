@@ -2,6 +2,8 @@
 own tests hold for the hot path (tests/golden/reference_kats.json, transcribed with file:line) and
 against the independent pure-Python Goldilocks vectors (tests/golden/goldilocks_vectors.json).
 CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -235,3 +237,24 @@ def test_goldilocks_conv_and_mul(gold64):
     assert list(oracle.poly_mul(GL, a3, b3)) == gold64["poly_mul_300x300_seed42_seed43"]
     e = gold64["eval_300_seed42_at_seed43_0"]
     assert oracle.poly_eval(GL, a3, e["x"]) == e["y"]
+
+
+def test_next_rows_against_independent_vectors():
+    """SURVEY §8f rows over the 64-bit field, pinned like the transforms: the C oracle against vectors from an
+    independent pure-Python generator (tests/golden/gen_next_rows.py → next_rows_vectors.json)."""
+    import json
+    from gpu_util import summary
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "next_rows_vectors.json")))
+    d = g["div_linear_5000_seed77"]
+    q, r = oracle.poly_divrem(GL, oracle.splitmix(GL, 77, 5000), [d["b0"], d["b1"]])
+    s = summary(q)
+    assert all(s[k] == d["quotient"][k] for k in s) and int(r[0]) == d["remainder"] and not r[1:].any()
+    d = g["divrem_40_by_5_seed1_seed2"]
+    q, r = oracle.poly_divrem(GL, oracle.splitmix(GL, 1, 40), oracle.splitmix(GL, 2, 5))
+    assert [int(v) for v in q] == d["q"] and [int(v) for v in r] == d["r"]
+    d = g["rs_msg5_n8_seed3"]
+    xs, ys = oracle.rs_encode(GL, d["msg"], 8)
+    assert [int(v) for v in xs] == d["xs"] and [int(v) for v in ys] == d["ys"]
+    assert [int(v) for v in oracle.rs_decode(GL, xs, ys, 5)] == d["msg"]
+    d = g["interpolate_12_seed71_seed72"]
+    assert [int(v) for v in oracle.rs_decode(GL, d["xs"], d["ys"], 12)] == d["coeffs"]
