@@ -1,4 +1,6 @@
 // api.cu — context management, profiling and memory helpers of the C ABI (include/ronk_b200.h).
+#include <cstdlib>
+
 #include "ronk_internal.h"
 
 using namespace ronk;
@@ -24,9 +26,24 @@ int ronk_ctx_create(ronk_ctx** out, int device, void* stream) {
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) return RONK_ECUDA;  // no CPU fallback: fail loudly
   if (device < 0 || device >= count) return RONK_EINVAL;
+  int prev = -1;
+  cudaGetDevice(&prev);  // the caller's current device is restored before returning
+  struct Restore {
+    int d;
+    ~Restore() { if (d >= 0) cudaSetDevice(d); }
+  } restore{prev};
   if (cudaSetDevice(device) != cudaSuccess) return RONK_ECUDA;
   ronk_ctx* ctx = new ronk_ctx();
   ctx->device = device;
+  auto env_int = [](const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+  };
+  ctx->tune.pf_dist = env_int("RONK_PF_DIST", 1);
+  ctx->tune.single_tile_log = env_int("RONK_SINGLE_TILE_LOG", 12);
+  ctx->tune.tile1 = env_int("RONK_TILE1", 14);
+  ctx->tune.tile2 = env_int("RONK_TILE2", 13);
+  ctx->tune.tile_adapt = env_int("RONK_TILE_ADAPT", 1);
   ctx->stream = (cudaStream_t)stream;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return RONK_ECUDA; }
@@ -46,7 +63,7 @@ int ronk_ctx_create(ronk_ctx** out, int device, void* stream) {
 
 int ronk_ctx_destroy(ronk_ctx* ctx) {
   if (!ctx) return RONK_OK;
-  cudaSetDevice(ctx->device);
+  ronk::DeviceGuard _dg(ctx);
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->plans) {
     NttPlan& p = kv.second;
@@ -77,6 +94,7 @@ int ronk_ctx_destroy(ronk_ctx* ctx) {
 }
 
 int ronk_ctx_set_stream(ronk_ctx* ctx, void* stream) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx) return RONK_EINVAL;
   RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->stream = (cudaStream_t)stream;
@@ -84,6 +102,7 @@ int ronk_ctx_set_stream(ronk_ctx* ctx, void* stream) {
 }
 
 int ronk_sync(ronk_ctx* ctx) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx) return RONK_EINVAL;
   RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return RONK_OK;
@@ -93,12 +112,14 @@ const char* ronk_last_error(ronk_ctx* ctx) { return ctx ? ctx->err.c_str() : "nu
 uint64_t ronk_launch_count(ronk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int ronk_prof_enable(ronk_ctx* ctx, int on) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx) return RONK_EINVAL;
   ctx->prof = on != 0;
   return RONK_OK;
 }
 
 int ronk_prof_fetch(ronk_ctx* ctx, char (*names)[32], float* ms, int max) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx) return 0;
   cudaStreamSynchronize(ctx->stream);
   int n = 0;
@@ -118,23 +139,27 @@ int ronk_prof_fetch(ronk_ctx* ctx, char (*names)[32], float* ms, int max) {
 }
 
 int ronk_dev_alloc(ronk_ctx* ctx, void** dptr, size_t bytes) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || !dptr) return RONK_EINVAL;
   RONK_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
   return RONK_OK;
 }
 int ronk_dev_free(ronk_ctx* ctx, void* dptr) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx) return RONK_EINVAL;
   RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   RONK_CUDA(ctx, cudaFree(dptr));
   return RONK_OK;
 }
 int ronk_memcpy_h2d(ronk_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx) return RONK_EINVAL;
   RONK_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return RONK_OK;
 }
 int ronk_memcpy_d2h(ronk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx) return RONK_EINVAL;
   RONK_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -142,31 +167,33 @@ int ronk_memcpy_d2h(ronk_ctx* ctx, void* dst_host, const void* src_dev, size_t b
 }
 
 int ronk_memcpy_d2d(ronk_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx) return RONK_EINVAL;
   RONK_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return RONK_OK;
 }
 
 int ronk_ipc_export(ronk_ctx* ctx, const void* dptr, uint8_t handle[64]) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || !dptr || !handle) return set_err(ctx, RONK_EINVAL, "null argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   cudaIpcMemHandle_t h;
-  RONK_CUDA(ctx, cudaSetDevice(ctx->device));
   RONK_CUDA(ctx, cudaIpcGetMemHandle(&h, const_cast<void*>(dptr)));
   std::memcpy(handle, &h, 64);
   return RONK_OK;
 }
 
 int ronk_ipc_open(ronk_ctx* ctx, const uint8_t handle[64], void** dptr) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || !dptr || !handle) return set_err(ctx, RONK_EINVAL, "null argument");
   cudaIpcMemHandle_t h;
   std::memcpy(&h, handle, 64);
-  RONK_CUDA(ctx, cudaSetDevice(ctx->device));
   RONK_CUDA(ctx, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
   return RONK_OK;
 }
 
 int ronk_ipc_close(ronk_ctx* ctx, void* dptr) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx) return RONK_EINVAL;
   RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   RONK_CUDA(ctx, cudaIpcCloseMemHandle(dptr));

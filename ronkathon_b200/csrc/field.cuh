@@ -174,6 +174,72 @@ struct GoldilocksField {
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
     return reduce_words(r0, r1, r2, r3);
   }
+  // ---- a · 2^S for a compile-time S: three single-correction forms (round 2) ---------------------
+  // Every form ends in ONE canonical add/sub (one EPS correction) and needs no wide multiply; the
+  // round-1 form (shift to 96 bits, then the generic two-correction word reduction) is kept behind
+  // RONK_SHIFT_V2=0 for A/B runs.  Derivations, with B = 2^32, B² ≡ B - 1, B³ ≡ -1 and
+  // 2^-32 ≡ -EPS (mod p); each was checked exhaustively over S against big-integer arithmetic
+  // (tools/shift_formulas.py) before it was written as PTX:
+  //  A  0 < S < 32   x·2^S = y0 + y1·B + y2·B²,  y2 < 2^S:   ≡ (y1:y0) + y2·EPS.
+  //                  (y2·EPS) + EPS = (y2 : ~y2), so the "a + (b + EPS), no carry → -EPS" add needs
+  //                  just one NOT; the result is canonical even when (y1:y0) ≥ p because y2·EPS ≤ EPS².
+  //  B  32 ≤ S < 64  x·2^S = (y0 + y1·B + y2·B²)·B ≡ (y0 + y1)·B - (y1 + y2); with y0 + y1 = S0 + c·B
+  //                  this is ((S0 + c) : 0) - (y1 + y2 + c): both operands canonical → one sub.
+  //  C  64 ≤ S < 96  k = 96 - S ∈ (0, 32]:  x·2^S = -x·2^-k,  x·2^-k = (x >> k) + v - v·B with
+  //                  v = (x0 << (32-k)) mod B  →  x·2^S = sub((v : 0), (x >> k) + v).
+  template <int S>
+  static __device__ __forceinline__ u64 shl_a(u32 a0, u32 a1) {  // 0 < S < 32
+    const u32 y0 = a0 << S, y1 = __funnelshift_l(a0, a1, S), y2 = a1 >> (32 - S);
+    u32 r0, r1;
+    asm("{\n\t.reg .u32 m, bw, n2;\n\t"
+        "not.b32 n2, %4;\n\t"
+        "add.cc.u32 %0, %2, n2;\n\t"
+        "addc.cc.u32 %1, %3, %4;\n\t"
+        "addc.u32 m, 0xFFFFFFFF, 0;\n\t"      // carry - 1: 0 or 0xFFFFFFFF (= EPS·[no carry])
+        RONK_TAIL_ADD("%0", "%1") "}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(y0), "r"(y1), "r"(y2));
+    return ((u64)r1 << 32) | r0;
+  }
+  template <int SP>
+  static __device__ __forceinline__ u64 shl_b(u32 a0, u32 a1) {  // S = 32 + SP, 0 ≤ SP < 32
+    u32 y0, y1, y2;
+    if constexpr (SP == 0) { y0 = a0; y1 = a1; y2 = 0u; }
+    else { y0 = a0 << SP; y1 = __funnelshift_l(a0, a1, SP); y2 = a1 >> (32 - SP); }
+    u32 r0, r1;
+    asm("{\n\t.reg .u32 s0, hi, b0, b1, m, bw;\n\t"
+        "add.cc.u32 s0, %2, %3;\n\t"          // y0 + y1 = s0 + c·B
+        "addc.u32 hi, s0, 0;\n\t"             // s0 + c  (≤ 2^32 - 1)
+        "addc.cc.u32 b0, %3, %4;\n\t"         // y1 + y2 + c
+        "addc.u32 b1, 0, 0;\n\t"
+        "sub.cc.u32 %0, 0, b0;\n\t"           // (hi : 0) - (b1 : b0)
+        "subc.cc.u32 %1, hi, b1;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        RONK_TAIL_SUB("%0", "%1") "}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(y0), "r"(y1), "r"(y2));
+    return ((u64)r1 << 32) | r0;
+  }
+  template <int K>
+  static __device__ __forceinline__ u64 shl_c(u64 a) {  // S = 96 - K, 0 < K ≤ 32
+    const u32 a0 = (u32)a;
+    const u64 xh = a >> K;
+    const u32 v = (K == 32) ? a0 : (a0 << (32 - K));
+    u32 r0, r1;
+    asm("{\n\t.reg .u32 t0, t1, m, bw;\n\t"
+        "add.cc.u32 t0, %2, %4;\n\t"          // (x >> k) + v  < p, no carry out
+        "addc.u32 t1, %3, 0;\n\t"
+        "sub.cc.u32 %0, 0, t0;\n\t"           // (v : 0) - that
+        "subc.cc.u32 %1, %4, t1;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        RONK_TAIL_SUB("%0", "%1") "}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"((u32)xh), "r"((u32)(xh >> 32)), "r"(v));
+    return ((u64)r1 << 32) | r0;
+  }
+#ifndef RONK_SHIFT_V2
+#define RONK_SHIFT_V2 1
+#endif
   // a · 2^S for a compile-time S in [0, 192), on 32-bit words (2^96 ≡ -1).
   template <int S>
   __device__ __forceinline__ u64 mul_pow2(u64 a) const {
@@ -182,6 +248,10 @@ struct GoldilocksField {
       return a;
     } else if constexpr (S >= 96) {
       return neg(mul_pow2<S - 96>(a));
+    } else if constexpr (RONK_SHIFT_V2 != 0) {
+      if constexpr (S < 32) return shl_a<S>((u32)a, (u32)(a >> 32));
+      else if constexpr (S < 64) return shl_b<S - 32>((u32)a, (u32)(a >> 32));
+      else return shl_c<96 - S>(a);
     } else {
       const u32 a0 = (u32)a, a1 = (u32)(a >> 32);
       constexpr int s = S % 32;

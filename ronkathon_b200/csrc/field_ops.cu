@@ -248,28 +248,36 @@ int ronk_root_of_unity(uint64_t p, uint64_t g, uint64_t n, uint64_t* out) {
 }
 
 int ronk_field_add_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   return binop<OP_ADD>(ctx, p, (const u64*)a, (const u64*)b, (u64*)out, n, "field_add");
 }
 int ronk_field_sub_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   return binop<OP_SUB>(ctx, p, (const u64*)a, (const u64*)b, (u64*)out, n, "field_sub");
 }
 int ronk_field_mul_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   return binop<OP_MUL>(ctx, p, (const u64*)a, (const u64*)b, (u64*)out, n, "field_mul");
 }
 int ronk_field_div_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   return binop<OP_DIV>(ctx, p, (const u64*)a, (const u64*)b, (u64*)out, n, "field_div");
 }
 int ronk_field_neg_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, uint64_t* out, size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   return unop<UOP_NEG>(ctx, p, (const u64*)a, (u64*)out, n, 0, "field_neg");
 }
 int ronk_field_inv_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, uint64_t* out, size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   return unop<UOP_INV>(ctx, p, (const u64*)a, (u64*)out, n, 0, "field_inv");
 }
 int ronk_field_pow_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, uint64_t e, uint64_t* out, size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   return unop<2>(ctx, p, (const u64*)a, (u64*)out, n, e, "field_pow");
 }
 
 int ronk_field_powers_u64(ronk_ctx* ctx, uint64_t p, uint64_t base, uint64_t scale, uint64_t* out, size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || (n && !out)) return set_err(ctx, RONK_EINVAL, "null argument");
   RONK_TRY(validate_modulus(ctx, p));
   if (base >= p || scale >= p) return set_err(ctx, RONK_EINVAL, "non-canonical argument");
@@ -290,6 +298,7 @@ int ronk_field_powers_u64(ronk_ctx* ctx, uint64_t p, uint64_t base, uint64_t sca
 
 int ronk_ntt_strided_small_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* data, uint32_t log_g, size_t stride,
                                size_t count, int inverse) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || (count && !data)) return set_err(ctx, RONK_EINVAL, "null argument");
   RONK_TRY(validate_modulus(ctx, p));
   if (g == 0 || g >= p) return set_err(ctx, RONK_EINVAL, "generator out of range");
@@ -323,6 +332,7 @@ int ronk_ntt_strided_small_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* 
 
 int ronk_ntt_cross_rank_fused_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t* const* peer_bufs,
                                   uint32_t log_g, uint32_t rank, uint32_t log_n, uint64_t* out) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || !peer_bufs || !out) return set_err(ctx, RONK_EINVAL, "null argument");
   RONK_TRY(validate_modulus(ctx, p));
   if (g == 0 || g >= p) return set_err(ctx, RONK_EINVAL, "generator out of range");
@@ -366,6 +376,7 @@ int ronk_ntt_cross_rank_fused_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, const u
 }
 
 int ronk_splitmix_fill_u64(ronk_ctx* ctx, uint64_t p, uint64_t seed, uint64_t* out, size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || (n && !out) || p == 0) return set_err(ctx, RONK_EINVAL, "bad argument");
   if (n == 0) return RONK_OK;
   {
@@ -387,6 +398,7 @@ static int host_stage(ronk_ctx* ctx, size_t n, u64** da, u64** db, u64** dout) {
 
 int ronk_field_binop_u64_host(ronk_ctx* ctx, int op, uint64_t p, const uint64_t* a, const uint64_t* b, uint64_t* out,
                               size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || (n && (!a || !b || !out))) return set_err(ctx, RONK_EINVAL, "null argument");
   if (n == 0) return RONK_OK;
   u64 *da, *db, *dout;
@@ -408,6 +420,7 @@ int ronk_field_binop_u64_host(ronk_ctx* ctx, int op, uint64_t p, const uint64_t*
 }
 
 int ronk_field_unop_u64_host(ronk_ctx* ctx, int op, uint64_t p, const uint64_t* a, uint64_t* out, size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || (n && (!a || !out))) return set_err(ctx, RONK_EINVAL, "null argument");
   if (n == 0) return RONK_OK;
   u64 *da, *db, *dout;
@@ -423,6 +436,7 @@ int ronk_field_unop_u64_host(ronk_ctx* ctx, int op, uint64_t p, const uint64_t* 
 }
 
 int ronk_field_pow_u64_host(ronk_ctx* ctx, uint64_t p, const uint64_t* a, uint64_t e, uint64_t* out, size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || (n && (!a || !out))) return set_err(ctx, RONK_EINVAL, "null argument");
   if (n == 0) return RONK_OK;
   u64 *da, *db, *dout;

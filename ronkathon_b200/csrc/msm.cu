@@ -193,6 +193,7 @@ extern "C" {
 
 int ronk_msm_pluto_ext(ronk_ctx* ctx, const uint8_t* points, size_t n_points, const uint8_t* scalars, size_t n_scalars,
                        uint8_t out[4]) {
+  ronk::DeviceGuard _dg(ctx);
   if (!out) return set_err(ctx, RONK_EINVAL, "null argument");
   u32 res = PT_INF;
   RONK_TRY(msm_device(ctx, points, n_points, scalars, n_scalars, nullptr, &res));
@@ -202,6 +203,7 @@ int ronk_msm_pluto_ext(ronk_ctx* ctx, const uint8_t* points, size_t n_points, co
 
 int ronk_msm_pluto_ext_buckets(ronk_ctx* ctx, const uint8_t* points, size_t n_points, const uint8_t* scalars,
                                size_t n_scalars, uint8_t buckets[68]) {
+  ronk::DeviceGuard _dg(ctx);
   if (!buckets) return set_err(ctx, RONK_EINVAL, "null argument");
   u32 b[17];
   RONK_TRY(msm_device(ctx, points, n_points, scalars, n_scalars, b, nullptr));
@@ -211,6 +213,7 @@ int ronk_msm_pluto_ext_buckets(ronk_ctx* ctx, const uint8_t* points, size_t n_po
 
 int ronk_msm_pluto_ext_host(ronk_ctx* ctx, const uint8_t* points, size_t n_points, const uint8_t* scalars,
                             size_t n_scalars, uint8_t out[4]) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || !out || (n_scalars && (!points || !scalars))) return set_err(ctx, RONK_EINVAL, "null argument");
   if (n_points < n_scalars) return set_err(ctx, RONK_EINVAL, "srs shorter than coefficients (kzg/setup.rs:53)");
   DevBytes P, S;
@@ -222,6 +225,7 @@ int ronk_msm_pluto_ext_host(ronk_ctx* ctx, const uint8_t* points, size_t n_point
 }
 
 int ronk_msm_combine_buckets_host(ronk_ctx* ctx, const uint8_t* buckets, size_t n_sets, uint8_t out[4]) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || !out || (n_sets && !buckets)) return set_err(ctx, RONK_EINVAL, "null argument");
   if (n_sets > (1u << 20)) return set_err(ctx, RONK_EUNSUPPORTED, "too many bucket sets");
   const size_t words = n_sets * 17;
@@ -276,12 +280,15 @@ static int point_op_host(ronk_ctx* ctx, int op, const uint8_t* a, const uint8_t*
 }
 
 int ronk_point_add_pluto_ext_host(ronk_ctx* ctx, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   return point_op_host(ctx, 0, a, b, nullptr, out, n);
 }
 int ronk_point_neg_pluto_ext_host(ronk_ctx* ctx, const uint8_t* a, uint8_t* out, size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   return point_op_host(ctx, 1, a, nullptr, nullptr, out, n);
 }
 int ronk_point_smul_pluto_ext_host(ronk_ctx* ctx, const uint8_t* a, const uint8_t* scalars, uint8_t* out, size_t n) {
+  ronk::DeviceGuard _dg(ctx);
   return point_op_host(ctx, 2, a, nullptr, scalars, out, n);
 }
 

@@ -90,18 +90,10 @@ static int build_plan(ronk_ctx* ctx, const F& f, u64 p, u64 g, u32 log_n, NttPla
 template <class F, int MODE, bool INV, int NTHR, int MINB, bool BOUNDED, bool FMUL>
 static int launch_tile_nb(ronk_ctx* ctx, const F& f, const NttTileArgs& A0, u32 tiles, const char* name) {
   NttTileArgs A = A0;
-  if (MODE == MODE_PASS1) {
-    static int pf = -1;  // RONK_PF_DIST: prefetch distance in units of co-resident CTAs (default 1, 0 = off)
-    if (pf < 0) {
-      const char* s = getenv("RONK_PF_DIST");
-      pf = s ? atoi(s) : 1;
-    }
-    A.prefetch_dist = (u32)pf * (u32)ctx->sm_count * (u32)MINB;
-  }
+  if (MODE == MODE_PASS1) A.prefetch_dist = (u32)ctx->tune.pf_dist * (u32)ctx->sm_count * (u32)MINB;
   const size_t smem = ((size_t)1 << A.tile_log) * sizeof(u64) + (size_t)A.tw_words * sizeof(u64) + 16;
-  // set on every launch: the attribute is per device, and several contexts may live in one process
-  RONK_CUDA(ctx, cudaFuncSetAttribute(ntt_tile_kernel<F, MODE, INV, NTHR, MINB, BOUNDED, FMUL>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  // the attribute is per device: set once per (context, instantiation)
+  RONK_TRY(ensure_smem_attr(ctx, ntt_tile_kernel<F, MODE, INV, NTHR, MINB, BOUNDED, FMUL>, 226 * 1024));
   {
     LaunchScope ls(ctx, name);
     ntt_tile_kernel<F, MODE, INV, NTHR, MINB, BOUNDED, FMUL><<<tiles, NTHR, smem, ctx->stream>>>(f, A);
@@ -149,8 +141,7 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
   if (src_len >= ((u64)1 << log_n)) src_len = NTT_UNBOUNDED;
   if (dst_len >= ((u64)1 << log_n)) dst_len = NTT_UNBOUNDED;
   if (!pl.two_pass) {
-    u32 cap = 12;
-    if (const char* s = getenv("RONK_SINGLE_TILE_LOG")) cap = (u32)atoi(s);
+    const u32 cap = (u32)ctx->tune.single_tile_log;
     NttTileArgs A =
         ntt_args_single(data, mul, pl.tw1_2d[INV ? 1 : 0], pl.scale_inv, log_n, (u64)batch << log_n, INV, cap, &tiles);
     A.src = src;
@@ -161,15 +152,8 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
   }
   const size_t bytes = ((size_t)batch << log_n) * sizeof(u64);
   RONK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, bytes));
-  static int pref1 = 0, pref2 = 0, adapt = 1;  // preferred tile sizes (log2); RONK_TILE1 / RONK_TILE2 for experiments
-  if (!pref1) {
-    const char* s1 = getenv("RONK_TILE1");
-    const char* s2 = getenv("RONK_TILE2");
-    const char* s3 = getenv("RONK_TILE_ADAPT");
-    pref1 = s1 ? atoi(s1) : 14;  // measured best on B200: strided pass-1 reads want 32-byte segments
-    pref2 = s2 ? atoi(s2) : 13;
-    adapt = s3 ? atoi(s3) : 1;
-  }
+  // preferred tile sizes (log2): 14 / 13 measured best on B200 (strided pass-1 reads want 32-byte segments)
+  const int pref1 = ctx->tune.tile1, pref2 = ctx->tune.tile2, adapt = ctx->tune.tile_adapt;
   // The preferred sizes are tuned for grids of ≥ 1000 tiles.  A mid-size job (one 2^20 transform is 64 tiles of
   // 2^14) would leave most SMs idle, so shrink the tiles until the grid fills the GPU, but never below 4 columns
   // in pass 1 (32-byte segments) / 2 in pass 2.
@@ -253,18 +237,19 @@ using namespace ronk;
 
 extern "C" int ronk_ntt_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* data, uint32_t log_n, uint32_t batch,
                             int inverse) {
+  ronk::DeviceGuard _dg(ctx);
   return ntt_device(ctx, p, g, (u64*)data, nullptr, log_n, batch, inverse);
 }
 
 extern "C" int ronk_ntt_mul_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* data, const uint64_t* mul,
                                 uint32_t log_n, uint32_t batch) {
+  ronk::DeviceGuard _dg(ctx);
   if (!mul) return set_err(ctx, RONK_EINVAL, "null multiplier");
   return ntt_device(ctx, p, g, (u64*)data, (const u64*)mul, log_n, batch, 0);
 }
 
 static int pipeline_init(ronk_ctx* ctx) {
   if (ctx->copy_in) return RONK_OK;
-  RONK_CUDA(ctx, cudaSetDevice(ctx->device));
   RONK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
   RONK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
   for (int i = 0; i < ronk_ctx::kSlots; i++) {
@@ -276,6 +261,7 @@ static int pipeline_init(ronk_ctx* ctx) {
 }
 
 extern "C" int ronk_ntt_u64_host_wait(ronk_ctx* ctx, int slot) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || slot < 0 || slot >= ronk_ctx::kSlots) return set_err(ctx, RONK_EINVAL, "bad slot");
   if (!ctx->slot_pending[slot]) return RONK_OK;
   RONK_CUDA(ctx, cudaEventSynchronize(ctx->ev_d2h[slot]));
@@ -285,6 +271,7 @@ extern "C" int ronk_ntt_u64_host_wait(ronk_ctx* ctx, int slot) {
 
 extern "C" int ronk_ntt_u64_host_submit(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* host_data, uint32_t log_n,
                                         uint32_t batch, int inverse, int slot) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || !host_data) return set_err(ctx, RONK_EINVAL, "null argument");
   if (slot < 0 || slot >= ronk_ctx::kSlots) return set_err(ctx, RONK_EINVAL, "bad slot");
   if (log_n > 26) return set_err(ctx, RONK_EUNSUPPORTED, "log_n > 26 not supported");
@@ -317,6 +304,7 @@ extern "C" int ronk_ntt_u64_host_submit(ronk_ctx* ctx, uint64_t p, uint64_t g, u
 
 extern "C" int ronk_ntt_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* host_data, uint32_t log_n,
                                  uint32_t batch, int inverse) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || !host_data) return set_err(ctx, RONK_EINVAL, "null argument");
   if (((size_t)batch << log_n) == 0) return RONK_OK;
   RONK_TRY(ronk_ntt_u64_host_submit(ctx, p, g, host_data, log_n, batch, inverse, 0));

@@ -70,13 +70,16 @@ __global__ void lagrange_eval_kernel(const F f, const u64* c, const u64* nodes, 
   u64 acc = 0, lx = 1 % f.modulus();
   for (u32 j = t; j < n; j += blockDim.x) {
     lx = f.mul(lx, f.sub(x, nodes[j]));
+    // The reference builds EVERY weight first (mod.rs:386-393), so a repeated node panics in F::ONE.div
+    // whatever x is — also for the terms the fold later discards.
+    u64 wden = 1 % f.modulus();  // w_j^-1 = Π_{m≠j} (x_j - x_m)
+    for (u32 m = 0; m < n; m++)
+      if (m != j) wden = f.mul(wden, f.sub(nodes[j], nodes[m]));
+    if (wden == 0) { atomicExch(flag, 1); continue; }
     if (jstar < n && j <= jstar) {
       if (j == jstar) acc = f.add(acc, c[j]);
       continue;
     }
-    u64 wden = 1 % f.modulus();  // w_j^-1 = Π_{m≠j} (x_j - x_m)
-    for (u32 m = 0; m < n; m++)
-      if (m != j) wden = f.mul(wden, f.sub(nodes[j], nodes[m]));
     const u64 den = f.mul(wden, f.sub(x, nodes[j]));
     if (den == 0) { atomicExch(flag, 1); continue; }
     acc = f.add(acc, f.mul(c[j], field_pow(f, den, f.modulus() - 2)));
@@ -520,29 +523,35 @@ extern "C" {
 
 int ronk_poly_mul_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t* a, size_t da, const uint64_t* b,
                       size_t db, uint64_t* c) {
+  ronk::DeviceGuard _dg(ctx);
   return poly_mul_device(ctx, p, g, (const u64*)a, da, (const u64*)b, db, (u64*)c);
 }
 
 int ronk_poly_add_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, size_t da, const uint64_t* b, size_t db,
                       uint64_t* out) {
+  ronk::DeviceGuard _dg(ctx);
   return poly_addsub<false>(ctx, p, (const u64*)a, da, (const u64*)b, db, (u64*)out);
 }
 int ronk_poly_sub_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, size_t da, const uint64_t* b, size_t db,
                       uint64_t* out) {
+  ronk::DeviceGuard _dg(ctx);
   return poly_addsub<true>(ctx, p, (const u64*)a, da, (const u64*)b, db, (u64*)out);
 }
 
 int ronk_poly_eval_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* coeffs, size_t d, const uint64_t* xs, size_t m,
                        uint64_t* out) {
+  ronk::DeviceGuard _dg(ctx);
   return poly_eval_device(ctx, p, (const u64*)coeffs, d, (const u64*)xs, m, (u64*)out);
 }
 
 int ronk_dft_u64(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t* in, uint64_t n, uint64_t* out) {
+  ronk::DeviceGuard _dg(ctx);
   return dft_device(ctx, p, g, (const u64*)in, n, (u64*)out);
 }
 
 int ronk_poly_div_linear_u64(ronk_ctx* ctx, uint64_t p, const uint64_t* a, size_t d, uint64_t b0, uint64_t b1,
                              uint64_t* q, uint64_t* rem) {
+  ronk::DeviceGuard _dg(ctx);
   return div_linear_device(ctx, p, (const u64*)a, d, b0, b1, (u64*)q, (u64*)rem);
 }
 
@@ -564,6 +573,7 @@ struct DevBuf {  // frees on scope exit
 
 int ronk_poly_mul_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t* a, size_t da, const uint64_t* b,
                            size_t db, uint64_t* c) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || !a || !b || !c) return set_err(ctx, RONK_EINVAL, "null argument");
   if (da == 0 || db == 0) return set_err(ctx, RONK_EINVAL, "empty polynomial (D + D2 - 1 underflows)");
   DevBuf A, B, C;
@@ -576,6 +586,7 @@ int ronk_poly_mul_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t
 
 int ronk_poly_eval_u64_host(ronk_ctx* ctx, uint64_t p, const uint64_t* coeffs, size_t d, const uint64_t* xs, size_t m,
                             uint64_t* out) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || (m && (!xs || !out)) || (d && !coeffs)) return set_err(ctx, RONK_EINVAL, "null argument");
   DevBuf C, X, O;
   RONK_TRY(up(ctx, &C.p, coeffs, d));
@@ -586,6 +597,7 @@ int ronk_poly_eval_u64_host(ronk_ctx* ctx, uint64_t p, const uint64_t* coeffs, s
 }
 
 int ronk_dft_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t* in, uint64_t n, uint64_t* out) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || !in || !out) return set_err(ctx, RONK_EINVAL, "null argument");
   DevBuf I, O;
   RONK_TRY(up(ctx, &I.p, in, n));
@@ -596,6 +608,7 @@ int ronk_dft_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t* in,
 
 int ronk_poly_lagrange_eval_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, const uint64_t* coeffs, size_t n,
                                      uint64_t x, uint64_t* out) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || !coeffs || !out) return set_err(ctx, RONK_EINVAL, "null argument");
   RONK_TRY(validate_modulus(ctx, p));
   if (g == 0 || g >= p || x >= p) return set_err(ctx, RONK_EINVAL, "argument out of range");
@@ -619,11 +632,16 @@ int ronk_poly_lagrange_eval_u64_host(ronk_ctx* ctx, uint64_t p, uint64_t g, cons
     lagrange_eval_kernel<MontField><<<1, 256, 0, ctx->stream>>>(f, C.p, N.p, (u32)n, x, O.p, ctx->d_flag);
   }
   RONK_TRY(check_launch(ctx, "lagrange_eval_kernel"));
-  return down(ctx, out, O.p, 1);
+  RONK_CUDA(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  RONK_TRY(down(ctx, out, O.p, 1));  // synchronises the stream
+  if (*ctx->h_flag)  // mod.rs:386-393: F::ONE.div(x_j - x_m) panics when two nodes coincide (g not of order n)
+    return set_err(ctx, RONK_EINVAL, "Lagrange evaluate: repeated node (the reference divides by zero)");
+  return RONK_OK;
 }
 
 int ronk_poly_interpolate_u64_host(ronk_ctx* ctx, uint64_t p, const uint64_t* xs, const uint64_t* ys, size_t k,
                                    uint64_t* out) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || (k && (!xs || !ys || !out))) return set_err(ctx, RONK_EINVAL, "null argument");
   RONK_TRY(validate_modulus(ctx, p));
   if (k == 0) return RONK_OK;
@@ -650,6 +668,7 @@ int ronk_poly_interpolate_u64_host(ronk_ctx* ctx, uint64_t p, const uint64_t* xs
 
 int ronk_poly_divrem_u64_host(ronk_ctx* ctx, uint64_t p, const uint64_t* a, size_t da, const uint64_t* b, size_t db,
                               uint64_t* q, uint64_t* r) {
+  ronk::DeviceGuard _dg(ctx);
   if (!ctx || (da && (!a || !q || !r)) || (db && !b)) return set_err(ctx, RONK_EINVAL, "null argument");
   RONK_TRY(validate_modulus(ctx, p));
   if (da > 0x7FFFFFF0ULL || db > 0x7FFFFFF0ULL) return set_err(ctx, RONK_EUNSUPPORTED, "polynomial too long");

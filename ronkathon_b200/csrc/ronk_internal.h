@@ -8,6 +8,7 @@
 #include <map>
 #include <string>
 #include <tuple>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/ronk_b200.h"
@@ -36,8 +37,17 @@ struct NttPlan {
 
 }  // namespace ronk
 
+// Tuning switches, read from the environment ONCE at ronk_ctx_create (never on the launch path).
+struct ronk_tune {
+  int pf_dist = 1;          // RONK_PF_DIST: pass-1 L2 prefetch distance in waves of co-resident CTAs (0 = off)
+  int single_tile_log = 12; // RONK_SINGLE_TILE_LOG: preferred tile size when several small transforms share a tile
+  int tile1 = 14, tile2 = 13, tile_adapt = 1;  // RONK_TILE1 / RONK_TILE2 / RONK_TILE_ADAPT
+};
+
 struct ronk_ctx {
   int device = 0;
+  ronk_tune tune;
+  std::unordered_set<const void*> smem_attr_done;  // kernels whose >48 KiB dynamic-smem attribute is set on `device`
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   std::string err;
@@ -81,6 +91,28 @@ inline int set_err(ronk_ctx* ctx, int code, const std::string& msg) {
     if (_rc != RONK_OK) return _rc; \
   } while (0)
 
+// Binds the calling thread to the context's device for the duration of one C-ABI call and restores the
+// caller's device on exit (contexts for several GPUs may coexist in one process; the caller — torch, a
+// Rust host — keeps its own current device).  Every extern "C" entry point that takes a ctx opens with it,
+// so allocations, attribute calls and launches inside the call all land on ctx->device.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const ronk_ctx* ctx) {
+    if (!ctx) return;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device) switched = cudaSetDevice(ctx->device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// Opt a kernel into > 48 KiB of dynamic shared memory, once per (context, kernel).
+template <class K>
+inline int ensure_smem_attr(ronk_ctx* ctx, K kernel, int bytes);
+
 // Brackets a kernel launch with the launch counter and (optionally) profiling events.
 struct LaunchScope {
   ronk_ctx* ctx;
@@ -88,8 +120,7 @@ struct LaunchScope {
   cudaEvent_t start = nullptr, stop = nullptr;
   const char* name;
   LaunchScope(ronk_ctx* c, const char* n) : ctx(c), on(c->prof), name(n) {
-    cudaSetDevice(ctx->device);  // contexts for several devices may coexist in one process
-    ctx->launches++;
+    ctx->launches++;  // the device is already bound by the entry point's DeviceGuard
     if (on) {
       cudaEventCreate(&start);
       cudaEventCreate(&stop);
@@ -108,6 +139,16 @@ struct LaunchScope {
     }
   }
 };
+
+template <class K>
+inline int ensure_smem_attr(ronk_ctx* ctx, K kernel, int bytes) {
+  const void* key = reinterpret_cast<const void*>(kernel);
+  if (ctx->smem_attr_done.count(key)) return RONK_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return set_err(ctx, RONK_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+  ctx->smem_attr_done.insert(key);
+  return RONK_OK;
+}
 
 inline int check_launch(ronk_ctx* ctx, const char* what) {
   cudaError_t e = cudaGetLastError();

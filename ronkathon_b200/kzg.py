@@ -27,7 +27,9 @@ def _pack(points) -> np.ndarray:
 def commit(coeffs, g1_srs) -> AffinePoint:
     """kzg/setup.rs:48-60: Σ g1_srs[i]·coeffs[i]; asserts g1_srs.len() >= coeffs.len()."""
     pts = _pack(g1_srs)
-    sc = np.array([int(getattr(c, "value", c)) for c in coeffs], dtype=np.uint8)
+    # coefficients are PlutoScalarField values; raw ints are reduced as PlutoScalarField::new does
+    # (prime/mod.rs:48-51: value % P) — never wrapped by the uint8 cast
+    sc = np.array([int(getattr(c, "value", c)) % 17 for c in coeffs], dtype=np.uint8)
     out = np.empty(4, dtype=np.uint8)
     n_pts = len(pts) // 4
     # the zip stops at the shorter sequence, so only the first len(coeffs) points are shipped
@@ -43,3 +45,24 @@ def open_(coeffs, eval_point, g1_srs) -> AffinePoint:
     divisor = Polynomial([(-z).value, 1], PlutoScalarField)
     q = poly / divisor
     return commit([int(v) for v in q.coefficients], g1_srs)
+
+
+def commit_lagrange(evaluations, g1_srs) -> AffinePoint:
+    """Commit to a polynomial given in the LAGRANGE basis over the 2^k-th roots of unity of F17 — the form in
+    which the PLONK compiler emits its selector / permutation polynomials (compiler/program.rs:118-226,
+    `Polynomial<Lagrange<PlutoScalarField>, PlutoScalarField, GROUP_ORDER>`).  The prover step the reference
+    never wrote: Lagrange → monomial by the inverse transform (polynomial/mod.rs:430-453, on the GPU), then
+    kzg::commit (kzg/setup.rs:48-60, the MSM kernel)."""
+    from .polynomial import Lagrange
+    poly = evaluations if isinstance(evaluations, Polynomial) else Polynomial(evaluations, PlutoScalarField, Lagrange)
+    if poly.basis is not Lagrange:
+        raise _lib.RonkPanic(1, "commit_lagrange expects a Lagrange-basis polynomial")
+    mono = poly.ifft()
+    return commit([int(v) for v in mono.coefficients], g1_srs)
+
+
+def commit_preprocessed(polys: dict, g1_srs) -> dict:
+    """Commitments to a `CommonPreprocessedInput` (compiler/program.rs:59-63: ql, qr, qm, qo, qc, s1, s2, s3),
+    each given as GROUP_ORDER evaluations."""
+    return {name: commit_lagrange(ev, g1_srs) for name, ev in polys.items()}
+
