@@ -87,4 +87,21 @@ extern "C" {
   pub fn ronk_msm_combine_buckets_host(ctx: *mut ronk_ctx, buckets: *const u8, n_sets: usize, out: *mut u8) -> c_int;
 
   pub fn ronk_splitmix_fill_u64(ctx: *mut ronk_ctx, p: u64, seed: u64, out: *mut u64, n: usize) -> c_int;
+
+  // multi-GPU modes (one context per GPU; NCCL inside the library).  `id` is RONK_NCCL_UNIQUE_ID_BYTES = 128 bytes:
+  // made on rank 0, carried to the other ranks by the host (e.g. MPI_Bcast), then every rank calls ronk_dist_init.
+  pub fn ronk_dist_unique_id(id: *mut u8) -> c_int;
+  pub fn ronk_dist_init(ctx: *mut ronk_ctx, id: *const u8, rank: c_int, world: c_int) -> c_int;
+  pub fn ronk_dist_init_comm(ctx: *mut ronk_ctx, nccl_comm: *mut c_void, rank: c_int, world: c_int) -> c_int;
+  pub fn ronk_dist_finalize(ctx: *mut ronk_ctx) -> c_int;
+  pub fn ronk_dist_rank(ctx: *mut ronk_ctx, rank: *mut c_int, world: *mut c_int) -> c_int;
+  pub fn ronk_dist_barrier(ctx: *mut ronk_ctx) -> c_int;
+  pub fn ronk_dist_shard_range(total: u64, rank: c_int, world: c_int, lo: *mut u64, hi: *mut u64) -> c_int;
+  pub fn ronk_ntt_u64_batch_sharded(ctx: *mut ronk_ctx, p: u64, g: u64, shard: *mut u64, log_n: u32, total_batch: u64, inverse: c_int, lo: *mut u64, hi: *mut u64) -> c_int;
+  pub fn ronk_ntt_u64_dist(ctx: *mut ronk_ctx, p: u64, g: u64, local: *mut u64, log_n: u32, batch: u32, flavour: c_int) -> c_int;
+  pub fn ronk_msm_pluto_ext_dist(ctx: *mut ronk_ctx, points: *const u8, n_points: usize, scalars: *const u8, n_scalars: usize, out: *mut u8) -> c_int;
 }
+
+pub const RONK_NCCL_UNIQUE_ID_BYTES: usize = 128;
+pub const RONK_DIST_NCCL: c_int = 0;
+pub const RONK_DIST_FUSED: c_int = 1;

@@ -137,6 +137,39 @@ int ronk_ipc_open(ronk_ctx *ctx, const uint8_t handle[64], void **dptr);
 int ronk_ipc_close(ronk_ctx *ctx, void *dptr);
 int ronk_memcpy_d2d(ronk_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);
 
+/* ---- multi-GPU modes ---------------------------------------------------------
+ * The reference is single-threaded and has no distributed layer; these are the modes BASELINE.json's
+ * north_star adds around its hot path: independent batches sharded with no collective, the top log2(G)
+ * stages of a transform across G GPUs with ONE exchange, and kzg::commit (src/kzg/setup.rs:48-60) over
+ * index-range shards.  One context per GPU (one process or host thread each); NCCL (libnccl.so.2,
+ * resolved with dlopen at the first call — RONK_ENCCL when absent) carries the collectives on the
+ * context's stream.  G = world must be a power of two ≤ 16. */
+#define RONK_NCCL_UNIQUE_ID_BYTES 128
+#define RONK_DIST_NCCL 0  /* exchange = grouped ncclSend/ncclRecv (all-to-all) */
+#define RONK_DIST_FUSED 1 /* exchange fused into the butterfly kernel: P2P loads from CUDA-IPC peer buffers */
+/* Bootstrap.  Rank 0 makes an id and the host carries its 128 bytes to every rank (MPI_Bcast, a TCP
+ * store, torch.distributed …); every rank then calls ronk_dist_init (collective).  Alternatively adopt
+ * an ncclComm_t the host already owns (not destroyed by ronk_dist_finalize). */
+int ronk_dist_unique_id(uint8_t id[RONK_NCCL_UNIQUE_ID_BYTES]);
+int ronk_dist_init(ronk_ctx *ctx, const uint8_t id[RONK_NCCL_UNIQUE_ID_BYTES], int rank, int world);
+int ronk_dist_init_comm(ronk_ctx *ctx, void *nccl_comm, int rank, int world);
+int ronk_dist_finalize(ronk_ctx *ctx);
+int ronk_dist_rank(ronk_ctx *ctx, int *rank, int *world);
+/* Stream-ordered barrier over the communicator (a 4-byte all-reduce): the host does not wait. */
+int ronk_dist_barrier(ronk_ctx *ctx);
+/* Contiguous range [lo, hi) of `total` units owned by `rank` (remainder spread over the first ranks). */
+int ronk_dist_shard_range(uint64_t total, int rank, int world, uint64_t *lo, uint64_t *hi);
+/* Polynomial::fft / ifft (src/polynomial/mod.rs:273-323, :430-484) of a batch sharded by contiguous
+ * ranges: this rank transforms its (hi - lo) × 2^log_n words at `shard` in place.  No collective. */
+int ronk_ntt_u64_batch_sharded(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *shard, uint32_t log_n, uint64_t total_batch, int inverse, uint64_t *lo, uint64_t *hi);
+/* Forward transforms of `batch` polynomials of 2^log_n coefficients, each spread CYCLICALLY over the
+ * ranks: `local` holds [batch][n/G] with local[b][j] = a_b[rank + G·j].  In place; on return
+ * local[b][q][k] = X_b[rank·(n/G²) + k + (n/G)·q], q < G, k < n/G² (block-cyclic).  Collective. */
+int ronk_ntt_u64_dist(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *local, uint32_t log_n, uint32_t batch, int flavour);
+/* kzg::commit over index-range shards: this rank's terms in, the full commitment out on every rank
+ * (RONK_EINVAL on every rank if any shard holds an invalid term).  Collective, synchronous. */
+int ronk_msm_pluto_ext_dist(ronk_ctx *ctx, const uint8_t *points, size_t n_points, const uint8_t *scalars, size_t n_scalars, uint8_t out[4]);
+
 /* ---- Polynomial<Monomial, F, D> ----------------------------------------------------------- */
 /* Mul — src/polynomial/arithmetic.rs:97-119.  c has da+db-1 coefficients (no trimming).
  * NTT path (pad → NTT, NTT∘pointwise → iNTT) when a power of two ≥ da+db-1 divides p-1 and
@@ -173,8 +206,10 @@ int ronk_poly_div_linear_u64(ronk_ctx *ctx, uint64_t p, const uint64_t *a, size_
 int ronk_point_add_pluto_ext_host(ronk_ctx *ctx, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
 int ronk_point_neg_pluto_ext_host(ronk_ctx *ctx, const uint8_t *a, uint8_t *out, size_t n);
 int ronk_point_smul_pluto_ext_host(ronk_ctx *ctx, const uint8_t *a, const uint8_t *scalars, uint8_t *out, size_t n);
-/* kzg::commit — src/kzg/setup.rs:48-60: Σ points[i]·scalars[i] for i < n_scalars as a Pippenger
- * bucket MSM.  RONK_EINVAL if n_points < n_scalars (the reference's assert), if a scalar ≥ 17
+/* kzg::commit — src/kzg/setup.rs:48-60: Σ points[i]·scalars[i] for i < n_scalars.  The group has
+ * 102² points and exponent 102, so the sum is taken as a point-indexed histogram of the scalars (one
+ * shared-memory atomicAdd per term) followed by c·P per occupied bin with the reference's addition law
+ * (RONK_MSM_HIST=0 selects the round-1 Pippenger bucket kernels).  RONK_EINVAL if n_points < n_scalars (the reference's assert), if a scalar ≥ 17
  * or if a point is off-curve.  `points`/`scalars` are device pointers, `out` is a 4-byte HOST
  * buffer; synchronous. */
 int ronk_msm_pluto_ext(ronk_ctx *ctx, const uint8_t *points, size_t n_points, const uint8_t *scalars, size_t n_scalars, uint8_t out[4]);

@@ -75,6 +75,16 @@ SIGNATURES = {
     "ronk_msm_pluto_ext_buckets": (i32, [vp, vp, sz, vp, sz, vp]),
     "ronk_msm_combine_buckets_host": (i32, [vp, vp, sz, vp]),
     "ronk_splitmix_fill_u64": (i32, [vp, u64, u64, vp, sz]),
+    "ronk_dist_unique_id": (i32, [vp]),
+    "ronk_dist_init": (i32, [vp, vp, i32, i32]),
+    "ronk_dist_init_comm": (i32, [vp, vp, i32, i32]),
+    "ronk_dist_finalize": (i32, [vp]),
+    "ronk_dist_rank": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
+    "ronk_dist_barrier": (i32, [vp]),
+    "ronk_dist_shard_range": (i32, [u64, i32, i32, p64, p64]),
+    "ronk_ntt_u64_batch_sharded": (i32, [vp, u64, u64, vp, u32, u64, i32, p64, p64]),
+    "ronk_ntt_u64_dist": (i32, [vp, u64, u64, vp, u32, u32, i32]),
+    "ronk_msm_pluto_ext_dist": (i32, [vp, vp, sz, vp, sz, vp]),
 }
 
 _lib = None

@@ -44,6 +44,9 @@ int ronk_ctx_create(ronk_ctx** out, int device, void* stream) {
   ctx->tune.tile1 = env_int("RONK_TILE1", 14);
   ctx->tune.tile2 = env_int("RONK_TILE2", 13);
   ctx->tune.tile_adapt = env_int("RONK_TILE_ADAPT", 1);
+  ctx->tune.tw_table = env_int("RONK_TW_TABLE", 1);
+  ctx->tune.msm_hist = env_int("RONK_MSM_HIST", 1);
+  ctx->tune.fast12 = env_int("RONK_FAST12", 1);
   ctx->stream = (cudaStream_t)stream;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return RONK_ECUDA; }
@@ -53,7 +56,7 @@ int ronk_ctx_create(ronk_ctx** out, int device, void* stream) {
     return RONK_EUNSUPPORTED;
   }
   if (cudaMalloc((void**)&ctx->d_flag, sizeof(int)) != cudaSuccess ||
-      cudaMallocHost((void**)&ctx->h_flag, 32 * sizeof(int)) != cudaSuccess) {  // h_flag[0] + 31 words of small results
+      cudaHostAlloc((void**)&ctx->h_flag, 32 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) {  // h_flag[0] + 31 words of small results
     delete ctx;
     return RONK_ENOMEM;
   }
@@ -65,6 +68,7 @@ int ronk_ctx_destroy(ronk_ctx* ctx) {
   if (!ctx) return RONK_OK;
   ronk::DeviceGuard _dg(ctx);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->dist) ronk_dist_finalize(ctx);
   for (auto& kv : ctx->plans) {
     NttPlan& p = kv.second;
     if (p.tw1) cudaFree(p.tw1);
@@ -75,6 +79,8 @@ int ronk_ctx_destroy(ronk_ctx* ctx) {
     }
     if (p.tw_lo) cudaFree(p.tw_lo);
     if (p.tw_hi_inv) cudaFree(p.tw_hi_inv);
+    for (int d = 0; d < 2; d++)
+      for (auto& t : p.tw_full[d]) cudaFree(t.second);
   }
   for (auto& r : ctx->prof_log) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
   for (int i = 0; i < ronk_ctx::kSlots; i++) {
@@ -87,6 +93,8 @@ int ronk_ctx_destroy(ronk_ctx* ctx) {
   if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ws2) cudaFree(ctx->ws2);
+  if (ctx->msm_ytab) cudaFree(ctx->msm_ytab);
+  if (ctx->msm_done) cudaFree(ctx->msm_done);
   if (ctx->d_flag) cudaFree(ctx->d_flag);
   if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
   delete ctx;

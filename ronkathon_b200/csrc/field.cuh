@@ -117,8 +117,30 @@ struct GoldilocksField {
   // words r0 + r1·B + r2·B² + r3·B³ (B = 2^32; B² ≡ B-1, B³ ≡ -1) → canonical residue:
   //   Y = r2·EPS + r0 (one IMAD.WIDE, ≤ p-1), W = r1·B ≤ p-1, so
   //   x = (Y - r3) + W = sub(sub(Y, r3), p - W) with p - W = (~r1 : 1) — two canonical subs.
+  // RONK_REDUCE_V2 (round 2): Y = r2·EPS + r0 is (r2 : r0) - r2 — one borrow chain (IADD3 + IMAD.X) instead
+  // of the wide multiply, which ptxas had lowered to IMAD.MOV + IMAD.HI + IADD3 + IMAD.X and which, like
+  // every IMAD.WIDE / IMAD.HI, holds the issue port for ≈ 4 cycles (profiles/r02a_pipe_microbench2.txt).
+#ifndef RONK_REDUCE_V2
+#define RONK_REDUCE_V2 1
+#endif
   static __device__ __forceinline__ u64 reduce_words(u32 r0, u32 r1, u32 r2, u32 r3) {
     u32 z0, z1;
+#if RONK_REDUCE_V2
+    asm("{\n\t.reg .u32 m, bw;\n\t"
+        "sub.cc.u32 %0, %2, %4;\n\t"        // (r2 : r0) - r2  =  r2·EPS + r0  (≥ 0: no borrow out of the pair)
+        "subc.u32 %1, %4, 0;\n\t"
+        "sub.cc.u32 %0, %0, %5;\n\t"        // t = Y - r3
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        RONK_TAIL_RED1("%0", "%1")
+        "add.cc.u32 %0, %0, 0xFFFFFFFF;\n\t" // t + (r1 : 0xFFFFFFFF)
+        "addc.cc.u32 %1, %1, %3;\n\t"
+        "addc.u32 m, 0xFFFFFFFF, 0;\n\t"     // carry - 1
+        RONK_TAIL_RED2("%0", "%1") "}"
+        : "=&r"(z0), "=&r"(z1)
+        : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
+    return ((u64)z1 << 32) | z0;
+#else
     // second step: t - (p - W) ≡ t + (r1 : 0xFFFFFFFF) (mod 2^64), and it borrows exactly when this
     // addition does NOT carry; m = carry - 1 is then the EPS mask of the "+p" correction.
     asm("{\n\t.reg .u64 y;\n\t.reg .u32 y0, y1, m, bw;\n\t"
@@ -135,6 +157,7 @@ struct GoldilocksField {
         : "=&r"(z0), "=&r"(z1)
         : "r"(r0), "r"(r1), "r"(r2), "r"(r3), "l"((u64)r0));
     return ((u64)z1 << 32) | z0;
+#endif
   }
   // three-word form (r3 = 0): x = Y + W only
   static __device__ __forceinline__ u64 reduce_words3(u32 r0, u32 r1, u32 r2) {

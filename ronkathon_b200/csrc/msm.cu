@@ -102,6 +102,148 @@ __global__ void __launch_bounds__(16 * MSM_FIN_LANES) msm_finish_kernel(const u3
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// kzg::commit as a point-indexed histogram (round 2).  E(F_101²): y² = x³ + 3 has 102² = 10 404 points and
+// exponent 102, so Σ s_i·P_i = Σ_P (c_P mod 102)·P with c_P = Σ_{i: P_i = P} s_i.  Each term then costs one
+// table lookup (validation) and one shared-memory atomicAdd — the kernel streams the 5 B/term once and is
+// HBM / atomic-bound instead of a chain of dependent affine additions (round 1: 73 GB/s at 2^20 terms).
+//   bin(P) = 2·(x0 + 101·x1) + ybit(y),  ybit(y) = y0 ? (y0 > 50) : (y1 > 50)   (y and -y get different bits)
+//   ytab[bin] = y0 | y1 << 8 of the curve point in that bin, 0xFFFF when the bin holds no point: a term is
+//               on the curve (curve/mod.rs:130-139) iff its coordinates are canonical and ytab[bin] == its y.
+//   msm_hist_kernel     per-CTA histogram in shared memory → partial[cta][MSM_BINS] (plain coalesced store)
+//   msm_hist_finish     one thread per bin: column sum mod 102, c·P by double-and-add with the reference's
+//                       addition law, CTA tree; the last CTA to finish reduces the CTA sums and writes result
+//                       and error flag straight into mapped pinned host memory (no memset / memcpy launches).
+constexpr u32 MSM_XS = Q101 * Q101;   // 10201 x values
+constexpr u32 MSM_BINS = 2 * MSM_XS;  // 20402
+constexpr u32 MSM_EXP = 102;          // group exponent of E(F_101²) ≅ (Z/102)²
+constexpr int MSM_HIST_THREADS = 1024;
+constexpr int MSM_FIN_THREADS = 256;
+
+RONK_DEV u32 y_bit(u32 y0, u32 y1) { return y0 ? (y0 > 50u) : (y1 > 50u); }
+
+// sq[idx(y²)] = y (either root), for every y in F_101²
+__global__ void msm_sqrt_table_kernel(uint16_t* sq) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MSM_XS) return;
+  const Gf y = {i % Q101, i / Q101};
+  const Gf y2 = gf_mul(y, y);
+  sq[y2.c0 + Q101 * y2.c1] = (uint16_t)(y.c0 | (y.c1 << 8));  // the two roots race; either is fine
+}
+__global__ void msm_ytab_kernel(const uint16_t* __restrict__ sq, uint16_t* __restrict__ ytab) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MSM_XS) return;
+  const Gf x = {i % Q101, i / Q101};
+  const Gf rhs = gf_add(gf_mul(gf_mul(x, x), x), Gf{3, 0});
+  const u32 r = sq[rhs.c0 + Q101 * rhs.c1];
+  uint16_t e0 = 0xFFFF, e1 = 0xFFFF;
+  if (r != 0xFFFFu) {
+    const Gf y = {r & 0xFF, r >> 8}, ny = gf_neg(y);
+    const uint16_t wy = (uint16_t)(y.c0 | (y.c1 << 8)), wn = (uint16_t)(ny.c0 | (ny.c1 << 8));
+    (y_bit(y.c0, y.c1) ? e1 : e0) = wy;
+    if (wn != wy) (y_bit(ny.c0, ny.c1) ? e1 : e0) = wn;
+  }
+  ytab[2 * i] = e0;
+  ytab[2 * i + 1] = e1;
+}
+
+__global__ void __launch_bounds__(MSM_HIST_THREADS, 1)
+msm_hist_kernel(const u32* __restrict__ points, const uint8_t* __restrict__ scalars, size_t n,
+                const uint16_t* __restrict__ ytab_g, u32* __restrict__ partial, volatile int* host_flag) {
+  extern __shared__ __align__(16) u32 msm_smem[];
+  u32* hist = msm_smem;                                      // [MSM_BINS]
+  uint16_t* ytab = reinterpret_cast<uint16_t*>(hist + MSM_BINS);  // [MSM_BINS]
+  const u32 t = threadIdx.x;
+  for (u32 i = t; i < MSM_BINS; i += MSM_HIST_THREADS) hist[i] = 0u;
+  {  // 40 804 bytes of table, 4 at a time
+    const u32* src = reinterpret_cast<const u32*>(ytab_g);
+    u32* dst = reinterpret_cast<u32*>(ytab);
+    for (u32 i = t; i < MSM_BINS / 2; i += MSM_HIST_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * MSM_HIST_THREADS;
+  bool bad = false;
+  constexpr int U = 4;  // loads in flight per thread
+  for (size_t i0 = (size_t)blockIdx.x * MSM_HIST_THREADS + t; i0 < n; i0 += stride * U) {
+    u32 w[U], s[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + (size_t)u * stride;
+      w[u] = (i < n) ? points[i] : PT_INF;
+      s[u] = (i < n) ? (u32)scalars[i] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (s[u] >= 17u) { bad = true; continue; }            // not an F17 residue
+      if (w[u] == PT_INF) continue;                         // Infinity · s = Infinity
+      if (__vcmpgeu4(w[u], 0x65656565u)) { bad = true; continue; }  // a coordinate ≥ 101
+      const u32 bin = 2u * ((w[u] & 0xFF) + Q101 * ((w[u] >> 8) & 0xFF)) + y_bit((w[u] >> 16) & 0xFF, w[u] >> 24);
+      if ((u32)ytab[bin] != (w[u] >> 16)) { bad = true; continue; }  // not on y² = x³ + 3
+      if (s[u]) atomicAdd(&hist[bin], s[u]);                // g1 * 0 = Infinity (curve/mod.rs:163-165)
+    }
+  }
+  if (bad) *host_flag = 1;
+  __syncthreads();
+  u32* out = partial + (size_t)blockIdx.x * MSM_BINS;
+  for (u32 i = t; i < MSM_BINS; i += MSM_HIST_THREADS) out[i] = hist[i];
+}
+
+// CTA tree over one point per thread (len = blockDim.x, a power of two); result in red[0].
+RONK_DEV void msm_cta_tree(u32* red, u32 t, u32 len, const uint8_t* inv) {
+#if defined(__CUDA_ARCH__)
+  for (u32 half = len / 2; half > 0; half >>= 1) {
+    if (t < half) red[t] = pt_add_t(red[t], red[t + half], inv);
+    __syncthreads();
+  }
+#endif
+}
+
+__global__ void __launch_bounds__(MSM_FIN_THREADS)
+msm_hist_finish_kernel(const u32* __restrict__ partial, u32 sets, const uint16_t* __restrict__ ytab,
+                       u32* __restrict__ cta_sum, u32* __restrict__ done_counter, volatile u32* host_result) {
+  __shared__ u32 red[MSM_FIN_THREADS];
+  __shared__ uint8_t inv[104];
+  __shared__ u32 is_last;
+  const u32 t = threadIdx.x;
+  build_inv_table(inv, t, MSM_FIN_THREADS);
+  const u32 bin = blockIdx.x * MSM_FIN_THREADS + t;
+  u32 c = 0;
+  if (bin < MSM_BINS)
+    for (u32 g = 0; g < sets; g++) c += partial[(size_t)g * MSM_BINS + bin];
+  c %= MSM_EXP;
+  __syncthreads();
+  u32 acc = PT_INF;
+  if (c) {  // the bin holds a curve point (only validated terms were counted)
+    const u32 xi = bin >> 1;
+    const u32 base = (xi % Q101) | ((xi / Q101) << 8) | ((u32)ytab[bin] << 16);
+    // c·P, most significant bit first: ≤ 6 doublings + ≤ 6 additions of the reference's affine law
+    for (int b = 31 - __clz(c); b >= 0; b--) {
+      acc = pt_add_t(acc, acc, inv);
+      if ((c >> b) & 1u) acc = pt_add_t(acc, base, inv);
+    }
+  }
+  red[t] = acc;
+  __syncthreads();
+  msm_cta_tree(red, t, MSM_FIN_THREADS, inv);
+  if (t == 0) {
+    cta_sum[blockIdx.x] = red[0];
+    __threadfence();
+    is_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  u32 mine = 0xFFFFFFFFu;  // Infinity
+  if (t < gridDim.x) mine = reinterpret_cast<volatile u32*>(cta_sum)[t];  // gridDim.x ≤ MSM_FIN_THREADS
+  red[t] = mine;
+  __syncthreads();
+  msm_cta_tree(red, t, MSM_FIN_THREADS, inv);
+  if (t == 0) {
+    host_result[0] = red[0];
+    *done_counter = 0u;  // ready for the next call
+  }
+}
+
 // element-wise curve ops (host API support). op: 0 add, 1 neg, 2 scalar-mul by repeated addition
 __global__ void point_op_kernel(int op, const u32* a, const u32* b, const uint8_t* sc, u32* out, size_t n, int* flag) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -137,7 +279,68 @@ static int msm_grid(ronk_ctx* ctx, size_t n) {
   return (int)ctas;
 }
 
-// device buckets[17] + result[1] for the first n_scalars terms
+// Histogram path: result of the first n_scalars terms (kzg::commit).  Two launches, no memset, no memcpy:
+// the kernels write the error flag and the result into mapped pinned host memory.
+static int msm_hist_device(ronk_ctx* ctx, const uint8_t* points, size_t n_points, const uint8_t* scalars, size_t n_scalars,
+                           u32* h_result) {
+  if (!ctx || (n_scalars && (!points || !scalars))) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (n_points < n_scalars) return set_err(ctx, RONK_EINVAL, "srs shorter than coefficients (kzg/setup.rs:53)");
+  if (((uintptr_t)points & 3) != 0) return set_err(ctx, RONK_EINVAL, "points must be 4-byte aligned");
+  if (n_scalars == 0) { *h_result = PT_INF; return RONK_OK; }   // empty sum = Infinity (curve/mod.rs:219-223)
+  constexpr size_t kSmem = MSM_BINS * sizeof(u32) + MSM_BINS * sizeof(uint16_t);
+  if (!ctx->msm_ytab) {  // one-time per context: curve tables, completion counter
+    uint16_t* sq = nullptr;
+    RONK_CUDA(ctx, cudaMalloc((void**)&sq, MSM_XS * sizeof(uint16_t)));
+    RONK_CUDA(ctx, cudaMalloc((void**)&ctx->msm_ytab, MSM_BINS * sizeof(uint16_t)));
+    RONK_CUDA(ctx, cudaMalloc((void**)&ctx->msm_done, sizeof(u32)));
+    RONK_CUDA(ctx, cudaMemsetAsync(sq, 0xFF, MSM_XS * sizeof(uint16_t), ctx->stream));
+    RONK_CUDA(ctx, cudaMemsetAsync(ctx->msm_done, 0, sizeof(u32), ctx->stream));
+    {
+      LaunchScope ls(ctx, "msm_tables");
+      msm_sqrt_table_kernel<<<(MSM_XS + 255) / 256, 256, 0, ctx->stream>>>(sq);
+      msm_ytab_kernel<<<(MSM_XS + 255) / 256, 256, 0, ctx->stream>>>(sq, (uint16_t*)ctx->msm_ytab);
+    }
+    RONK_TRY(check_launch(ctx, "msm table kernels"));
+    RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(sq);
+  }
+  RONK_TRY(ensure_smem_attr(ctx, msm_hist_kernel, (int)kSmem));
+  // one CTA per SM at most; each thread should see ≥ 8 terms before another CTA (and its 82 KB of partial
+  // histogram traffic) is worth it
+  size_t ctas = (n_scalars + (size_t)MSM_HIST_THREADS * 8 - 1) / ((size_t)MSM_HIST_THREADS * 8);
+  if (ctas > (size_t)ctx->sm_count) ctas = (size_t)ctx->sm_count;
+  if (ctas < 1) ctas = 1;
+  constexpr u32 fin_ctas = (MSM_BINS + MSM_FIN_THREADS - 1) / MSM_FIN_THREADS;  // 80
+  static_assert(fin_ctas <= MSM_FIN_THREADS, "final tree assumes one CTA sum per thread");
+  const size_t need = (ctas * MSM_BINS + fin_ctas) * sizeof(u32);
+  RONK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, need));
+  u32* partial = (u32*)ctx->ws;
+  u32* cta_sum = partial + ctas * MSM_BINS;
+  volatile u32* host = (volatile u32*)ctx->h_flag;  // mapped pinned: [0] = flag, [1] = result
+  host[0] = 0u;
+  host[1] = PT_INF;
+  u32* host_dev = nullptr;
+  RONK_CUDA(ctx, cudaHostGetDevicePointer((void**)&host_dev, (void*)ctx->h_flag, 0));
+  {
+    LaunchScope ls(ctx, "msm_hist");
+    msm_hist_kernel<<<(unsigned)ctas, MSM_HIST_THREADS, kSmem, ctx->stream>>>(
+        (const u32*)points, scalars, n_scalars, (const uint16_t*)ctx->msm_ytab, partial, (volatile int*)host_dev);
+  }
+  RONK_TRY(check_launch(ctx, "msm_hist_kernel"));
+  {
+    LaunchScope ls(ctx, "msm_hist_finish");
+    msm_hist_finish_kernel<<<fin_ctas, MSM_FIN_THREADS, 0, ctx->stream>>>(
+        partial, (u32)ctas, (const uint16_t*)ctx->msm_ytab, cta_sum, (u32*)ctx->msm_done, (volatile u32*)(host_dev + 1));
+  }
+  RONK_TRY(check_launch(ctx, "msm_hist_finish_kernel"));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (host[0]) return set_err(ctx, RONK_EINVAL, "off-curve point, non-canonical coordinate or scalar >= 17");
+  *h_result = host[1];
+  return RONK_OK;
+}
+
+// Bucket path (the 17 Pippenger bucket sums a rank contributes to a distributed commit, and the round-1 kernel
+// pair): device buckets[17] + result[1] for the first n_scalars terms
 static int msm_device(ronk_ctx* ctx, const uint8_t* points, size_t n_points, const uint8_t* scalars, size_t n_scalars,
                       u32* h_buckets /*17 or null*/, u32* h_result) {
   if (!ctx || (n_scalars && (!points || !scalars))) return set_err(ctx, RONK_EINVAL, "null argument");
@@ -196,7 +399,8 @@ int ronk_msm_pluto_ext(ronk_ctx* ctx, const uint8_t* points, size_t n_points, co
   ronk::DeviceGuard _dg(ctx);
   if (!out) return set_err(ctx, RONK_EINVAL, "null argument");
   u32 res = PT_INF;
-  RONK_TRY(msm_device(ctx, points, n_points, scalars, n_scalars, nullptr, &res));
+  if (ctx && ctx->tune.msm_hist) RONK_TRY(msm_hist_device(ctx, points, n_points, scalars, n_scalars, &res));
+  else RONK_TRY(msm_device(ctx, points, n_points, scalars, n_scalars, nullptr, &res));
   unpack_to_bytes(res, out);
   return RONK_OK;
 }

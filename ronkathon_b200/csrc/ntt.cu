@@ -3,6 +3,9 @@
 // replacing Polynomial::fft / ifft (src/polynomial/mod.rs:273-323, :430-484).
 #include <cstdlib>
 
+#include <type_traits>
+
+#include "ntt12_kernel.cuh"
 #include "ntt_kernel.cuh"
 #include "ronk_internal.h"
 
@@ -87,6 +90,34 @@ static int build_plan(ronk_ctx* ctx, const F& f, u64 p, u64 g, u32 log_n, NttPla
   return RONK_OK;
 }
 
+// n-word table of the inter-pass twiddles for one direction and one workspace layout (log2 C2), built on first use.
+// The plan lives in ctx->plans; the table pointer is cached there (mutable through the context).
+template <class F>
+static int interpass_table(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, bool inverse, u32 log_c2, const u64* tw_lo,
+                           const u64* tw_hi, const u64** out) {
+  NttPlan& pl = const_cast<NttPlan&>(pl_c);
+  auto& m = pl.tw_full[inverse ? 1 : 0];
+  auto it = m.find(log_c2);
+  if (it == m.end()) {
+    u64* tab = nullptr;
+    const u64 n = (u64)1 << pl.log_n;
+    if (cudaMalloc((void**)&tab, n * sizeof(u64)) != cudaSuccess) {
+      cudaGetLastError();
+      *out = nullptr;  // no memory for the table: the stepped form needs none
+      return RONK_OK;
+    }
+    {
+      LaunchScope ls(ctx, "interpass_table");
+      interpass_table_kernel<F><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+          f, tw_lo, tw_hi, pl.log_n, pl.log_n1, pl.log_n2, log_c2, pl.log_n1, inverse ? 1 : 0, tab);
+    }
+    RONK_TRY(check_launch(ctx, "interpass_table_kernel"));
+    it = m.emplace(log_c2, tab).first;
+  }
+  *out = it->second;
+  return RONK_OK;
+}
+
 template <class F, int MODE, bool INV, int NTHR, int MINB, bool BOUNDED, bool FMUL>
 static int launch_tile_nb(ronk_ctx* ctx, const F& f, const NttTileArgs& A0, u32 tiles, const char* name) {
   NttTileArgs A = A0;
@@ -117,11 +148,46 @@ static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 ti
   return launch_tile_nb<F, MODE, INV, NTHR, MINB, false, false>(ctx, f, A, tiles, name);
 }
 
+// The specialised 4096-point-per-tile kernel (ntt12_kernel.cuh): Goldilocks, unbounded, log_m = 12.
+template <int MODE, bool INV, int LC, int LC2, bool FMUL>
+static int launch12_one(ronk_ctx* ctx, const GoldilocksField& f, const NttTileArgs& A0, u32 tiles, const char* name) {
+  using L = N12<LC>;
+  NttTileArgs A = A0;
+  if (MODE == MODE_PASS1) A.prefetch_dist = (u32)ctx->tune.pf_dist * (u32)ctx->sm_count * (L::NTHR >= 512 ? 1u : 2u);
+  const size_t smem = (size_t)(L::TILE_WORDS + L::TW_WORDS) * sizeof(u64) + 16;
+  RONK_TRY(ensure_smem_attr(ctx, ntt12_kernel<GoldilocksField, MODE, INV, LC, LC2, FMUL>, (int)smem));
+  {
+    LaunchScope ls(ctx, name);
+    ntt12_kernel<GoldilocksField, MODE, INV, LC, LC2, FMUL><<<tiles, L::NTHR, smem, ctx->stream>>>(f, A);
+  }
+  return check_launch(ctx, name);
+}
+template <int MODE, bool INV>
+static int launch12(ronk_ctx* ctx, const GoldilocksField& f, const NttTileArgs& A, u32 tiles, const char* name) {
+  if constexpr (MODE == MODE_PASS1) {
+    if (A.log_c2 == 1) return launch12_one<MODE, INV, 2, 1, false>(ctx, f, A, tiles, name);
+    return launch12_one<MODE, INV, 2, 2, false>(ctx, f, A, tiles, name);
+  } else {
+    const bool fmul = !INV && (A.flags & NTT_FLAG_MUL);
+    if (INV && (A.flags & NTT_FLAG_MUL)) return RONK_EUNSUPPORTED;  // never requested: the fused multiply is forward-only
+    if (A.log_c == 1) {
+      if (fmul) return launch12_one<MODE, INV, 1, 1, !INV>(ctx, f, A, tiles, name);
+      return launch12_one<MODE, INV, 1, 1, false>(ctx, f, A, tiles, name);
+    }
+    if (fmul) return launch12_one<MODE, INV, 2, 1, !INV>(ctx, f, A, tiles, name);
+    return launch12_one<MODE, INV, 2, 1, false>(ctx, f, A, tiles, name);
+  }
+}
+
 // CTA shape: every thread owns 32 tile elements per round (two radix-16 groups, ≤128 registers, no
 // spills).  A 2^14 tile is one 512-thread CTA per SM; a 2^13 tile is a 256-thread CTA and two of
 // them share an SM, so one CTA's load/store phases overlap the other's butterflies.
 template <class F, int MODE, bool INV>
 static int launch_tile(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tiles, const char* name) {
+  if constexpr (std::is_same<F, GoldilocksField>::value && MODE != MODE_SINGLE) {
+    if (ctx->tune.fast12 && ntt12_applicable(A, MODE) && !(INV && (A.flags & NTT_FLAG_MUL)))
+      return launch12<MODE, INV>(ctx, f, A, tiles, name);
+  }
   const u32 groups = (1u << A.tile_log) / 16;
   if (groups >= 1024) return launch_tile_n<F, MODE, INV, 512, 1>(ctx, f, A, tiles, name);
   if (groups >= 512) return launch_tile_n<F, MODE, INV, 256, 2>(ctx, f, A, tiles, name);
@@ -134,7 +200,8 @@ static int launch_tile(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tile
 // result happen inside the load / store phases instead of in separate copy kernels.
 template <class F, bool INV>
 static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, const u64* mul, u32 batch,
-                   const u64* src = nullptr, u64 src_len = NTT_UNBOUNDED, u64 dst_len = NTT_UNBOUNDED) {
+                   const u64* src = nullptr, u64 src_len = NTT_UNBOUNDED, u64 dst_len = NTT_UNBOUNDED,
+                   u64 mul_mask = ~0ULL) {
   const u32 log_n = pl.log_n;
   u64 tiles = 0;
   if (!src) src = data;
@@ -147,6 +214,7 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
     A.src = src;
     A.src_len = src_len;
     A.dst_len = dst_len;
+    A.mul_mask = mul_mask;
     if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
     return launch_tile<F, MODE_SINGLE, INV>(ctx, f, A, (u32)tiles, INV ? "intt_single" : "ntt_single");
   }
@@ -171,10 +239,16 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
                                   log_n, batch, tile1, tile2, &tiles);
   A1.src_len = src_len;
   if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
+  if (ctx->tune.tw_table) {
+    const u64* tab = nullptr;
+    RONK_TRY(interpass_table(ctx, f, pl, INV, A1.log_c2, A1.tw_lo, A1.tw_hi, &tab));
+    A1.tw_full = tab;
+  }
   RONK_TRY((launch_tile<F, MODE_PASS1, INV>(ctx, f, A1, (u32)tiles, INV ? "intt_pass1" : "ntt_pass1")));
   // pass 2: N2-point transforms along the contiguous workspace tiles, natural-order output
   NttTileArgs A2 = ntt_args_pass2((const u64*)ctx->ws, data, mul, pl.tw2_2d[INV ? 1 : 0], log_n, batch, tile2, &tiles);
   A2.dst_len = dst_len;
+  A2.mul_mask = mul_mask;
   if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
   return launch_tile<F, MODE_PASS2, INV>(ctx, f, A2, (u32)tiles, INV ? "intt_pass2" : "ntt_pass2");
 }
@@ -182,7 +256,7 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
 template <class F>
 static int ntt_with_field(ronk_ctx* ctx, const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 log_n, u32 batch,
                           int inverse, const u64* src = nullptr, u64 src_len = NTT_UNBOUNDED,
-                          u64 dst_len = NTT_UNBOUNDED) {
+                          u64 dst_len = NTT_UNBOUNDED, u64 mul_mask = ~0ULL) {
   auto key = std::make_tuple((uint64_t)p, (uint64_t)g, (uint32_t)log_n);
   auto it = ctx->plans.find(key);
   if (it == ctx->plans.end()) {
@@ -190,8 +264,8 @@ static int ntt_with_field(ronk_ctx* ctx, const F& f, u64 p, u64 g, u64* data, co
     RONK_TRY(build_plan(ctx, f, p, g, log_n, &pl));
     it = ctx->plans.emplace(key, pl).first;
   }
-  return inverse ? run_ntt<F, true>(ctx, f, it->second, data, mul, batch, src, src_len, dst_len)
-                 : run_ntt<F, false>(ctx, f, it->second, data, mul, batch, src, src_len, dst_len);
+  return inverse ? run_ntt<F, true>(ctx, f, it->second, data, mul, batch, src, src_len, dst_len, mul_mask)
+                 : run_ntt<F, false>(ctx, f, it->second, data, mul, batch, src, src_len, dst_len, mul_mask);
 }
 
 // One transform, out of place: dst[0, dst_len) = NTT(src[0, src_len) zero-extended to 2^log_n) [⊙ mul].
@@ -208,6 +282,24 @@ int ntt_device_bounded(ronk_ctx* ctx, u64 p, u64 g, const u64* src, u64 src_len,
   MontField f;
   RONK_TRY(make_mont_field(ctx, p, g, inverse != 0, &f));
   return ntt_with_field(ctx, f, p, g, dst, mul, log_n, 1, inverse, src, src_len, dst_len);
+}
+
+// dst = NTT(src) ⊙ mul (forward), batch transforms, mul an n-word table shared by all of them (index & (n-1)).
+// src may equal dst.  Used by the distributed transform (dist.cu): the twiddle column ω_n'^(r·k) rides on the
+// store phase of the local transform instead of two extra passes over the data.
+int ntt_device_shared_mul(ronk_ctx* ctx, u64 p, u64 g, const u64* src, u64* dst, const u64* mul, u32 log_n, u32 batch) {
+  if (!ctx || !src || !dst) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (log_n == 0 || log_n > 26 || (p - 1) % ((u64)1 << log_n) != 0)
+    return set_err(ctx, RONK_EINVAL, "unsupported transform size");
+  if (batch == 0) return RONK_OK;
+  const u64 mask = mul ? (((u64)1 << log_n) - 1) : ~0ULL;
+  if (is_goldilocks_fast(p, g)) {
+    GoldilocksField f;
+    return ntt_with_field(ctx, f, p, g, dst, mul, log_n, batch, 0, src, NTT_UNBOUNDED, NTT_UNBOUNDED, mask);
+  }
+  MontField f;
+  RONK_TRY(make_mont_field(ctx, p, g, false, &f));
+  return ntt_with_field(ctx, f, p, g, dst, mul, log_n, batch, 0, src, NTT_UNBOUNDED, NTT_UNBOUNDED, mask);
 }
 
 int ntt_device(ronk_ctx* ctx, u64 p, u64 g, u64* data, const u64* mul, u32 log_n, u32 batch, int inverse) {

@@ -49,7 +49,9 @@ struct NttTileArgs {
   const u64* tw_lo;    // PASS1: ω_n^x, x ∈ [0, 2^log_lo)
   const u64* tw_hi;    // PASS1: ω_n^(y·2^log_lo) (· n^-1 for the inverse), y ∈ [0, n >> log_lo)
   const u64* tw_hi_plain;  // PASS1: the same table without the n^-1 factor (twiddle stepping ratio)
-  const u64* mul_src;  // optional point-wise multiplier, indexed like dst
+  const u64* tw_full;  // PASS1, optional: the whole inter-pass twiddle ω_n^(±j2·k1) [· n^-1], laid out like dst
+  const u64* mul_src;  // optional point-wise multiplier, indexed like dst (index & mul_mask)
+  u64 mul_mask;        // ~0: one multiplier word per output word; n-1: one n-word multiplier shared by the batch
   u64 scale;           // SINGLE + inverse: n^-1 in twiddle form
   u64 total;           // SINGLE: number of valid elements (batch·n)
   u32 tile_log, log_m, log_c;
@@ -353,7 +355,7 @@ RONK_DEV void ntt_store_phase(const F& f, const u64* smem, const NttTileArgs& A,
       if (ga >= A.total || (BOUNDED && ga >= A.dst_len)) continue;
       u64 v = smem[sw_t ^ swz(store_perm<MODE>(A, gj))];
       if (A.flags & NTT_FLAG_SCALE) v = f.mul_tw(v, A.scale);
-      if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[ga]);
+      if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[ga & A.mul_mask]);
       A.dst[ga] = v;
     }
   } else if (MODE == MODE_PASS1) {
@@ -370,12 +372,30 @@ RONK_DEV void ntt_store_phase(const F& f, const u64* smem, const NttTileArgs& A,
       const u32 j2 = (sub << lc) | c;
       const u32 k1_t = ((tid >> cl) << lc2) | k1_in;
       const u32 dk1 = (1u << (kk - cl)) << lc2;
+      const u64 dst_t = base + ((u64)(tid >> cl) << (A.log_n2 + lc2)) + ((u64)j2 << lc2) + k1_in;
+      const u64 ddst = (u64)(1u << (kk - cl)) << (A.log_n2 + lc2);
+      if (A.tw_full) {
+        // Table form: the twiddle of workspace word i is tw_full[i mod n] — one coalesced load at the store's own
+        // offset replaces the stepping multiply (a general multiply is 4 IMAD.WIDE + 13 ALU-pipe instructions; the
+        // kernel is integer-pipe-bound with HBM at < 20 %, so the extra 8 B/element of reads are nearly free).
+        const u64* tw_t = A.tw_full + (dst_t - base);
+        constexpr u32 TB = 8;
+        for (u32 j0 = 0; j0 < per_thread; j0 += TB) {
+          u64 w[TB];
+#pragma unroll
+          for (u32 i = 0; i < TB; i++) w[i] = ld_tw(tw_t + (u64)(j0 + i) * ddst);
+#pragma unroll
+          for (u32 i = 0; i < TB; i++) {
+            const u32 gj = (j0 + i) << kk;
+            A.dst[dst_t + (u64)(j0 + i) * ddst] = f.mul_tw(smem[sw_t ^ swz(store_perm<MODE>(A, gj))], w[i]);
+          }
+        }
+        return;
+      }
       u32 ex0 = j2 * k1_t, exd = j2 * dk1;
       if (INV) { ex0 = (0u - ex0) & nmask; exd = (0u - exd) & nmask; }
       u64 w = f.mul_tw(ld_tw(A.tw_lo + (ex0 & lomask)), ld_tw(A.tw_hi + (ex0 >> A.log_lo)));
       const u64 rho = f.mul_tw(ld_tw(A.tw_lo + (exd & lomask)), ld_tw(A.tw_hi_plain + (exd >> A.log_lo)));
-      const u64 dst_t = base + ((u64)(tid >> cl) << (A.log_n2 + lc2)) + ((u64)j2 << lc2) + k1_in;
-      const u64 ddst = (u64)(1u << (kk - cl)) << (A.log_n2 + lc2);
 #pragma unroll 4
       for (u32 j = 0; j < per_thread; j++) {
         const u32 gj = j << kk;
@@ -410,7 +430,7 @@ RONK_DEV void ntt_store_phase(const F& f, const u64* smem, const NttTileArgs& A,
       const u64 addr = addr_t + ((u64)(gj >> lc2) << A.log_n1);
       if (BOUNDED && addr >= A.dst_len) continue;
       u64 v = smem[sw_t ^ swz(store_perm<MODE>(A, gj))];
-      if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[addr]);
+      if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[addr & A.mul_mask]);
       A.dst[addr] = v;
     }
   }
@@ -475,7 +495,7 @@ RONK_DEV void ntt_store_phase_v0(const F& f, const u64* smem, const NttTileArgs&
       const u32 e = (bt << A.log_m) | bitrev(k, A.log_m);
       u64 v = smem[swz(e)];
       if (A.flags & NTT_FLAG_SCALE) v = f.mul_tw(v, A.scale);
-      if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[base + g]);
+      if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[(base + g) & A.mul_mask]);
       A.dst[base + g] = v;
     }
   } else if (MODE == MODE_PASS1) {
@@ -508,7 +528,7 @@ RONK_DEV void ntt_store_phase_v0(const F& f, const u64* smem, const NttTileArgs&
         for (int i = 0; i < SB; i++) {
           const u32 g = g0 + i * nthr;
           const u64 addr = base + (g & ((1u << lc2) - 1u)) + ((u64)(g >> lc2) << A.log_n1);
-          m[i] = (g < T && !(BOUNDED && addr >= A.dst_len)) ? A.mul_src[addr] : 0ULL;
+          m[i] = (g < T && !(BOUNDED && addr >= A.dst_len)) ? A.mul_src[addr & A.mul_mask] : 0ULL;
         }
 #pragma unroll
         for (int i = 0; i < SB; i++) {
@@ -527,7 +547,7 @@ RONK_DEV void ntt_store_phase_v0(const F& f, const u64* smem, const NttTileArgs&
         const u64 addr = base + k1_in + ((u64)k2 << A.log_n1);
         if (BOUNDED && addr >= A.dst_len) continue;
         u64 v = smem[swz(e)];
-        if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[addr]);
+        if (A.flags & NTT_FLAG_MUL) v = f.mul(v, A.mul_src[addr & A.mul_mask]);
         A.dst[addr] = v;
       }
     }
@@ -566,6 +586,7 @@ inline NttTileArgs ntt_args_single(u64* data, const u64* mul, const u64* tw, u64
   A.tw_tile = tw;
   A.tw_words = ntt_tw2d_layout(log_n, A.tw_off);
   A.mul_src = mul;
+  A.mul_mask = ~0ULL;
   A.scale = scale_inv;
   A.total = total;
   A.tile_log = tile_log;
@@ -617,6 +638,7 @@ inline NttTileArgs ntt_args_pass2(const u64* ws, u64* data, const u64* mul, cons
   A.tw_tile = tw2;
   A.tw_words = ntt_tw2d_layout(sh.log_n2, A.tw_off);
   A.mul_src = mul;
+  A.mul_mask = ~0ULL;
   A.tile_log = tile2;
   A.log_m = sh.log_n2;
   A.log_c = tile2 - sh.log_n2;
@@ -697,6 +719,24 @@ static __global__ void tw2d_gather_kernel(const u64* __restrict__ tw1d, u32 log_
   bool valid;
   const u32 idx = ntt_tw2d_source(log_m, w, inverse != 0, &valid);
   out[w] = valid ? tw1d[idx] : 0ULL;
+}
+
+// Full inter-pass twiddle table in the pass-1 workspace layout W[k1 / C2][j2][k1 % C2]:
+// out[i] = tw_lo[e & lomask] · tw_hi[e >> log_lo], e = ±j2·k1 mod n (tw_hi carries n^-1 for the inverse).
+template <class F>
+__global__ void interpass_table_kernel(const F f, const u64* __restrict__ tw_lo, const u64* __restrict__ tw_hi, u32 log_n,
+                                       u32 log_n1, u32 log_n2, u32 log_c2, u32 log_lo, int inverse, u64* __restrict__ out) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >> log_n) return;
+  const u32 k1_in = (u32)i & ((1u << log_c2) - 1u);
+  const u32 j2 = (u32)(i >> log_c2) & ((1u << log_n2) - 1u);
+  const u32 k1 = ((u32)(i >> (log_n2 + log_c2)) << log_c2) | k1_in;
+  const u32 nmask = (log_n >= 32) ? 0xFFFFFFFFu : ((1u << log_n) - 1u);
+  u32 ex = (j2 * k1) & nmask;
+  if (inverse) ex = (0u - ex) & nmask;
+  // product of two twiddle-form values is in twiddle form again for Goldilocks (plain residues); for the
+  // Montgomery policy mul_tw(a_plainR, b_R) = a·b·R — tw_lo is stored in twiddle form, so this stays in it too
+  out[i] = f.mul_tw(tw_lo[ex & ((1u << log_lo) - 1u)], tw_hi[ex >> log_lo]);
 }
 
 // tab[i] = to_tw(w^i · s) for i < count  (plan building; w, s plain residues)

@@ -33,6 +33,9 @@ struct NttPlan {
   u64* tw_lo = nullptr;      // ω_n^x, x < N1
   u64* tw_hi_inv = nullptr;  // ω_n^(y·N1) · n^-1
   u64 scale_inv = 0;         // n^-1, twiddle form (single-pass inverse)
+  // full inter-pass twiddle tables ω_n^(±j2·k1) [· n^-1] in the pass-1 workspace layout, per direction and
+  // per log2(C2) of that layout (built on first use; n words each)
+  std::map<u32, u64*> tw_full[2];
 };
 
 }  // namespace ronk
@@ -42,6 +45,9 @@ struct ronk_tune {
   int pf_dist = 1;          // RONK_PF_DIST: pass-1 L2 prefetch distance in waves of co-resident CTAs (0 = off)
   int single_tile_log = 12; // RONK_SINGLE_TILE_LOG: preferred tile size when several small transforms share a tile
   int tile1 = 14, tile2 = 13, tile_adapt = 1;  // RONK_TILE1 / RONK_TILE2 / RONK_TILE_ADAPT
+  int fast12 = 1;           // RONK_FAST12: the specialised 4096-point-per-tile kernel (ntt12_kernel.cuh) where it applies
+  int msm_hist = 1;         // RONK_MSM_HIST: kzg::commit through the point-indexed histogram (1) or the bucket kernels (0)
+  int tw_table = 1;         // RONK_TW_TABLE: inter-pass twiddles from an n-word table (1) or stepped w ← w·ρ (0)
 };
 
 struct ronk_ctx {
@@ -66,6 +72,9 @@ struct ronk_ctx {
   size_t slot_bytes[kSlots] = {};
   cudaEvent_t ev_h2d[kSlots] = {}, ev_compute[kSlots] = {}, ev_d2h[kSlots] = {};
   bool slot_pending[kSlots] = {};
+  void* dist = nullptr;      // ronk::DistState (dist.cu): communicator, peer mappings, staging — null until ronk_dist_init
+  void* msm_ytab = nullptr;  // uint16_t[20402]: y of the curve point in each histogram bin (msm.cu), built on first use
+  void* msm_done = nullptr;  // u32 completion counter of msm_hist_finish_kernel
   int* d_flag = nullptr;  // device error flag
   int* h_flag = nullptr;  // pinned host mirror: h_flag[0] = error flag, h_flag[1..31] = small results (msm.cu)
 };
@@ -180,6 +189,7 @@ int validate_modulus(ronk_ctx* ctx, u64 p);                                     
 
 // Internal device-pointer entry points used across translation units.
 int ntt_device(ronk_ctx* ctx, u64 p, u64 g, u64* data, const u64* mul, u32 log_n, u32 batch, int inverse);
+int ntt_device_shared_mul(ronk_ctx* ctx, u64 p, u64 g, const u64* src, u64* dst, const u64* mul, u32 log_n, u32 batch);
 int ntt_device_bounded(ronk_ctx* ctx, u64 p, u64 g, const u64* src, u64 src_len, u64* dst, u64 dst_len, const u64* mul,
                        u32 log_n, int inverse);
 

@@ -187,3 +187,62 @@ class FusedDistributedNTT:
         if self.buf:
             self.ctx.call("ronk_dev_free", self.buf)
             self.buf = None
+
+
+DIST_NCCL, DIST_FUSED = 0, 1
+
+
+class DistContext:
+    """The multi-GPU entry points of the C ABI (`ronk_dist_*`, `ronk_ntt_u64_dist`, `ronk_ntt_u64_batch_sharded`,
+    `ronk_msm_pluto_ext_dist`): the library owns the NCCL communicator, the IPC-exported exchange buffers and
+    the kernels; this class only carries the 128-byte ncclUniqueId from rank 0 to the other ranks over whatever
+    `torch.distributed` group the host already has (gloo or nccl) — the job a Rust host would give to MPI or a
+    TCP store."""
+
+    def __init__(self, ctx, group=None):
+        import ctypes as C
+        self.ctx, self.group = ctx, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        uid = (C.c_uint8 * 128)()
+        if self.rank == 0:
+            rc = _lib.lib().ronk_dist_unique_id(C.cast(uid, _lib.vp))
+            if rc != 0:
+                raise _lib.RonkError(rc, "ronk_dist_unique_id: libnccl.so.2 not available")
+        box = [bytes(uid)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        uid = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        ctx.call("ronk_dist_init", C.cast(uid, _lib.vp), self.rank, self.world)
+
+    def shard_range(self, total: int):
+        return shard_range(total, self.rank, self.world)
+
+    def ntt_batch_sharded(self, shard, log_n: int, total_batch: int, inverse: bool = False, p: int = GOLDILOCKS, g: int = 7):
+        """This rank's contiguous range of `total_batch` independent transforms, in place; no collective."""
+        import ctypes as C
+        lo, hi = C.c_uint64(), C.c_uint64()
+        self.ctx.call("ronk_ntt_u64_batch_sharded", p, g, _lib._ptr(shard), log_n, total_batch, int(inverse),
+                      C.byref(lo), C.byref(hi))
+        return lo.value, hi.value
+
+    def ntt_dist(self, local, log_n: int, batch: int = 1, flavour: int = DIST_FUSED, p: int = GOLDILOCKS, g: int = 7):
+        """`local` = [batch][n/G] with local[b][j] = a_b[rank + G·j]; in place → [batch][G][n/G²] block-cyclic."""
+        assert local.numel() == batch * ((1 << log_n) // self.world)
+        self.ctx.call("ronk_ntt_u64_dist", p, g, _lib._ptr(local), log_n, batch, flavour)
+        return local
+
+    def msm(self, points_shard, scalars_shard) -> bytes:
+        """kzg::commit over index-range shards (device tensors); the full commitment on every rank."""
+        import numpy as np
+        out = np.empty(4, dtype=np.uint8)
+        n = scalars_shard.numel()
+        self.ctx.call("ronk_msm_pluto_ext_dist", _lib._ptr(points_shard), n, _lib._ptr(scalars_shard), n, _lib._ptr(out))
+        return out.tobytes()
+
+    def barrier(self):
+        self.ctx.call("ronk_dist_barrier")
+
+    def close(self):
+        if self.ctx is not None:
+            self.ctx.call("ronk_dist_finalize")
+            self.ctx = None
+

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../ronkathon_b200/csrc/ntt12_kernel.cuh"
 #include "../../ronkathon_b200/csrc/ntt_kernel.cuh"
 
 using namespace ronk;
@@ -62,6 +63,8 @@ std::vector<u64> table2d(const std::vector<u64>& tw1d, u32 log_m, bool inverse) 
 // 0: the kernel's own per-mode choice (RONK_LOAD_V0_MASK / RONK_STORE_V0_MASK), 1: XOR-composed phases
 // everywhere, 2: per-element ("v0") phases everywhere
 int g_variant = 0;
+// Optional n-word inter-pass twiddle table (NttTileArgs::tw_full) for emu_ntt: 0 = stepped twiddles.
+int g_tw_table = 0;
 bool use_v0(int mask, int mode) { return g_variant == 0 ? ((mask >> mode) & 1) != 0 : g_variant == 2; }
 
 template <class F, int MODE, bool INV, bool BOUNDED, bool FMUL = false>
@@ -83,10 +86,50 @@ void run_tiles_b(const F& f, const NttTileArgs& A, u64 tiles) {
   }
 }
 
+// The specialised 4096-point-per-tile kernel (ntt12_kernel.cuh), phase by phase like ntt12_kernel itself.
+// g_fast12: 1 = take it wherever ntt.cu's launch_tile would (the product default), 0 = never.
+int g_fast12 = 1;
+u64 g_fast12_tiles = 0;  // tiles that went through it (so a test can tell the path was really taken)
+template <class F, int MODE, bool INV, int LC, int LC2, bool FMUL>
+void run_tiles12(const F& f, const NttTileArgs& A, u64 tiles) {
+  using L = N12<LC>;
+  std::vector<u64> smem(L::TILE_WORDS);
+  for (u64 tile = 0; tile < tiles; tile++) {
+    for (u32 t = 0; t < L::NTHR; t++) n12_load<MODE, LC>(smem.data(), A, (u32)tile, t);
+    for (u32 t = 0; t < L::NTHR; t++) n12_round<F, INV, LC, 0>(f, smem.data(), A.tw_tile, t);
+    for (u32 t = 0; t < L::NTHR; t++) n12_round<F, INV, LC, 1>(f, smem.data(), A.tw_tile, t);
+    for (u32 t = 0; t < L::NTHR; t++) n12_round<F, INV, LC, 2>(f, smem.data(), A.tw_tile, t);
+    for (u32 t = 0; t < L::NTHR; t++) {
+      if (MODE == MODE_PASS1) n12_store_pass1<F, INV, LC, LC2>(f, smem.data(), A, (u32)tile, t);
+      else n12_store_pass2<F, LC, FMUL>(f, smem.data(), A, (u32)tile, t);
+    }
+  }
+  g_fast12_tiles += tiles;
+}
+template <class F, int MODE, bool INV>
+bool try_tiles12(const F& f, const NttTileArgs& A, u64 tiles) {  // same dispatch as launch12() in ntt.cu
+  if (!g_fast12 || MODE == MODE_SINGLE || !ntt12_applicable(A, MODE) || (INV && (A.flags & NTT_FLAG_MUL))) return false;
+  if (MODE == MODE_PASS1) {
+    if (A.log_c2 == 1) run_tiles12<F, MODE, INV, 2, 1, false>(f, A, tiles);
+    else run_tiles12<F, MODE, INV, 2, 2, false>(f, A, tiles);
+    return true;
+  }
+  const bool fmul = !INV && (A.flags & NTT_FLAG_MUL);
+  if (A.log_c == 1) {
+    if (fmul) run_tiles12<F, MODE, INV, 1, 1, true>(f, A, tiles);
+    else run_tiles12<F, MODE, INV, 1, 1, false>(f, A, tiles);
+  } else {
+    if (fmul) run_tiles12<F, MODE, INV, 2, 1, true>(f, A, tiles);
+    else run_tiles12<F, MODE, INV, 2, 1, false>(f, A, tiles);
+  }
+  return true;
+}
+
 // src == nullptr: in place; otherwise the bounded out-of-place form of run_ntt() in ntt.cu (batch 1)
 // same choice of instantiation as launch_tile_n() in ntt.cu
 template <class F, int MODE, bool INV>
 void run_tiles(const F& f, const NttTileArgs& A, u64 tiles) {
+  if (try_tiles12<F, MODE, INV>(f, A, tiles)) return;
   const bool bounded = (MODE != MODE_PASS2 && A.src_len != NTT_UNBOUNDED) || (MODE != MODE_PASS1 && A.dst_len != NTT_UNBOUNDED);
   constexpr bool can_fmul = MODE == MODE_PASS2 && !INV;
   if (can_fmul && (A.flags & NTT_FLAG_MUL)) {
@@ -133,6 +176,21 @@ int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 l
   NttTileArgs A1 = ntt_args_pass1(src, ws.data(), tw1_2d.data(), tw_lo.data(), INV ? tw_hi_inv.data() : tw2.data(),
                                   tw2.data(), log_n, batch, tile1, tile2, &tiles);
   A1.src_len = src_len;
+  std::vector<u64> tw_full;
+  if (g_tw_table) {  // mirrors interpass_table_kernel
+    tw_full.resize(n);
+    const u64* thi = INV ? tw_hi_inv.data() : tw2.data();
+    for (u64 i = 0; i < n; i++) {
+      const u32 k1_in = (u32)i & ((1u << A1.log_c2) - 1u);
+      const u32 j2 = (u32)(i >> A1.log_c2) & ((1u << sh.log_n2) - 1u);
+      const u32 k1 = ((u32)(i >> (sh.log_n2 + A1.log_c2)) << A1.log_c2) | k1_in;
+      const u32 nmask = (log_n >= 32) ? 0xFFFFFFFFu : ((1u << log_n) - 1u);
+      u32 ex = (j2 * k1) & nmask;
+      if (INV) ex = (0u - ex) & nmask;
+      tw_full[i] = f.mul_tw(tw_lo[ex & ((1u << A1.log_lo) - 1u)], thi[ex >> A1.log_lo]);
+    }
+    A1.tw_full = tw_full.data();
+  }
   run_tiles<F, MODE_PASS1, INV>(f, A1, tiles);
   NttTileArgs A2 = ntt_args_pass2(ws.data(), data, mul, tw2_2d.data(), log_n, batch, tile2, &tiles);
   A2.dst_len = dst_len;
@@ -141,6 +199,61 @@ int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 l
 }
 
 }  // namespace
+
+
+// Bank-conflict audit of the additive layout of ntt12_kernel.cuh: worst multiplicity of an 8-byte bank within a
+// half-warp over every access of every phase (load, three rounds, both store forms); 1 = conflict-free.
+// Also checks that word() is injective on the tile and stays inside TILE_WORDS (returns -1 otherwise).
+template <int LC, int LC2>
+static int layout12_worst(int mode) {
+  using L = N12<LC>;
+  std::vector<int> seen(L::TILE_WORDS, 0);
+  for (u32 e = 0; e < L::T; e++) {
+    if (L::word(e) >= L::TILE_WORDS || seen[L::word(e)]++) return -1;
+  }
+  int worst = 1;
+  auto account = [&](const std::vector<u32>& words) {  // one access instruction of one half-warp
+    int cnt[16] = {0};
+    for (u32 w : words) cnt[w & 15]++;
+    for (int k = 0; k < 16; k++) worst = cnt[k] > worst ? cnt[k] : worst;
+  };
+  for (u32 hw = 0; hw < L::NTHR / 16; hw++) {
+    for (u32 j = 0; j < 32; j++) {  // load: e = tid + j·NTHR
+      std::vector<u32> w;
+      for (u32 l = 0; l < 16; l++) w.push_back(L::word(hw * 16 + l + (j << L::KK)));
+      account(w);
+    }
+    for (int R = 0; R < 3; R++) {
+      const u32 wb = LC + 8 - 4 * R;
+      for (u32 g = 0; g < 2; g++)
+        for (u32 q = 0; q < 16; q++) {
+          std::vector<u32> w;
+          for (u32 l = 0; l < 16; l++) {
+            const u32 t = hw * 16 + l + g * L::NTHR;
+            const u32 e0 = ((t >> wb) << (wb + 4)) | (t & ((1u << wb) - 1u));
+            w.push_back(L::word(e0 | (q << wb)));
+          }
+          account(w);
+        }
+    }
+    for (u32 j = 0; j < 32; j++) {  // store: tile index of output element g = tid + j·NTHR
+      std::vector<u32> w;
+      for (u32 l = 0; l < 16; l++) {
+        const u32 g = hw * 16 + l + (j << L::KK);
+        u32 e;
+        if (mode == MODE_PASS2) e = (bitrev12c(g >> LC) << LC) | (g & (L::C - 1u));
+        else {
+          const u32 cl = LC + LC2, rem = g & ((1u << cl) - 1u);
+          const u32 k1 = ((g >> cl) << LC2) | (rem & ((1u << LC2) - 1u));
+          e = (bitrev12c(k1) << LC) | (rem >> LC2);
+        }
+        w.push_back(L::word(e));
+      }
+      account(w);
+    }
+  }
+  return worst;
+}
 
 extern "C" {
 
@@ -159,6 +272,17 @@ int emu_ntt(uint64_t p, uint64_t g, uint64_t* data, const uint64_t* mul, uint32_
 }
 
 void emu_set_variant(int v) { g_variant = v; }
+void emu_set_fast12(int on) { g_fast12 = on; }
+uint64_t emu_fast12_tiles(void) { return g_fast12_tiles; }
+
+void emu_set_tw_table(int on) { g_tw_table = on; }
+int emu_layout12_worst_conflict(int mode, int lc, int lc2) {
+  if (mode == MODE_PASS1 && lc == 2 && lc2 == 1) return layout12_worst<2, 1>(mode);
+  if (mode == MODE_PASS1 && lc == 2 && lc2 == 2) return layout12_worst<2, 2>(mode);
+  if (mode == MODE_PASS2 && lc == 1) return layout12_worst<1, 1>(mode);
+  if (mode == MODE_PASS2 && lc == 2) return layout12_worst<2, 1>(mode);
+  return -2;
+}
 
 // Bounded out-of-place transform (ntt_device_bounded): dst[0, dst_len) = NTT(src[0, src_len) ‖ zeros) [⊙ mul].
 int emu_ntt_bounded(uint64_t p, uint64_t g, const uint64_t* src, uint64_t src_len, uint64_t* dst, uint64_t dst_len,

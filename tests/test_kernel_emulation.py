@@ -22,7 +22,8 @@ def emu():
     so = os.path.join(HERE, "emu", "libntt_emu.so")
     hdr = os.path.join(HERE, "..", "ronkathon_b200", "csrc", "ntt_kernel.cuh")
     hdr2 = os.path.join(HERE, "..", "ronkathon_b200", "csrc", "field.cuh")
-    newest = max(os.path.getmtime(x) for x in (src, hdr, hdr2))
+    hdr3 = os.path.join(HERE, "..", "ronkathon_b200", "csrc", "ntt12_kernel.cuh")
+    newest = max(os.path.getmtime(x) for x in (src, hdr, hdr2, hdr3))
     if not os.path.exists(so) or os.path.getmtime(so) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src])
     lib = C.CDLL(so)
@@ -32,6 +33,7 @@ def emu():
     lib.emu_field_op.argtypes = [C.c_uint64, C.c_int, P64, P64, P64, C.c_uint64, C.c_int]
     lib.emu_gl_w16.argtypes = [C.c_uint64, P64]
     lib.emu_swizzle_worst_conflict.argtypes = [C.c_uint32, C.c_uint32]
+    lib.emu_fast12_tiles.restype = C.c_uint64
     return lib
 
 
@@ -230,3 +232,44 @@ def test_additive_layout_design_audit():
         assert ok and words <= int(1.07 * (1 << (12 + c)))
         bad, _ = audit.check_shape(f"{mode} c={c} unpadded", mode, 12, c, c2, 512, [], verbose=False)
         assert not bad
+
+
+# ---- the specialised 4096-point-per-tile kernel (ntt12_kernel.cuh) ------------------------------------------
+@pytest.mark.parametrize("mode,lc,lc2", [(1, 2, 1), (1, 2, 2), (2, 1, 1), (2, 2, 1)])
+def test_additive_layout_is_injective_and_conflict_free(emu, mode, lc, lc2):
+    """word(e) of ntt12_kernel.cuh: injective on the tile, inside TILE_WORDS, and every shared-memory access of
+    every phase (tile load, three radix-16 rounds, un-bit-reversing store) hits 16 distinct 8-byte banks per
+    half-warp."""
+    assert emu.emu_layout12_worst_conflict(mode, lc, lc2) == 1
+
+
+@pytest.mark.parametrize("log_n,tiles,table", [(24, (14, 13), 0), (24, (14, 13), 1), (24, (14, 14), 0), (23, (14, 13), 1)])
+def test_fast12_two_pass_transform_matches_oracle(emu, log_n, tiles, table):
+    """2^24 = 4096 × 4096 (both passes through the specialised kernel, with the pass-2 tile at 2 and at 4 columns, the
+    inter-pass twiddle stepped and from the n-word table) and 2^23 = 4096 × 2048 (pass 1 specialised, pass 2
+    generic): forward against the oracle, then the inverse back to the input."""
+    a = oracle.splitmix(GL, 42, 1 << log_n)
+    emu.emu_set_tw_table(table)
+    try:
+        before = emu.emu_fast12_tiles()
+        X = emu_ntt(emu, GL, 7, a, log_n, tiles=tiles)
+        assert emu.emu_fast12_tiles() > before, "the specialised path was not taken"
+        assert np.array_equal(X, oracle.ntt_fast(GL, a))
+        assert np.array_equal(emu_ntt(emu, GL, 7, X, log_n, inverse=True, tiles=tiles), a)
+    finally:
+        emu.emu_set_tw_table(0)
+
+
+def test_fast12_agrees_with_generic_kernel_and_fused_multiply(emu):
+    """Same 2^24 transform through the generic tile kernel (fast12 off) and the specialised one, plus the fused
+    point-wise multiply of pass 2 (NTT_FLAG_MUL → the FMUL instantiation)."""
+    a, b = oracle.splitmix(GL, 5, 1 << 24), oracle.splitmix(GL, 6, 1 << 24)
+    fast = emu_ntt(emu, GL, 7, a, 24, tiles=(14, 13), mul=b)
+    emu.emu_set_fast12(0)
+    try:
+        slow = emu_ntt(emu, GL, 7, a, 24, tiles=(14, 13), mul=b)
+    finally:
+        emu.emu_set_fast12(1)
+    assert np.array_equal(fast, slow)
+    assert np.array_equal(fast, oracle.vec_mul(GL, oracle.ntt_fast(GL, a), b))
+

@@ -14,6 +14,7 @@
 #define LOP(i) "lop3.b32 %" S(i) ",%" S(i) ",%12,%13,0x96;"
 #define SHFO(i) "shf.l.wrap.b32 %" S(i) ",%" S(i) ",%12,%13;"
 #define IMAD(i) "mad.lo.u32 %" S(i) ",%" S(i) ",%12,%13;"
+#define IHI(i) "mad.hi.u32 %" S(i) ",%" S(i) ",%12,%13;"
 template <int MODE>
 __global__ void __launch_bounds__(256) k(unsigned long long* out, unsigned long long* cyc, unsigned m, unsigned m2) {
   unsigned a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -37,13 +38,16 @@ __global__ void __launch_bounds__(256) k(unsigned long long* out, unsigned long 
     if (MODE == 10) asm volatile(IMAD(0) IMAD(1) IMAD(2) WIDE(8) IMAD(3) IMAD(4) IMAD(5) WIDE(9) OPS);       // 6 IMAD : 2 WIDE
     if (MODE == 11) asm volatile(LOP(0) LOP(1) IMAD(4) IMAD(5) WIDE(8) LOP(2) LOP(3) IMAD(6) IMAD(7) WIDE(9) OPS);  // 4 ALU : 4 IMAD : 2 WIDE
     if (MODE == 12) asm volatile(LOP(0) IMAD(4) SHFO(1) IMAD(5) LOP(2) IMAD(6) SHFO(3) IMAD(7) OPS);         // 4 ALU(lop/shf) : 4 IMAD
+    if (MODE == 14) asm volatile(A8(IHI) OPS);                                         // 8 IMAD.HI
+    if (MODE == 15) asm volatile(LOP(0) IHI(4) LOP(1) IHI(5) LOP(2) IHI(6) LOP(3) IHI(7) OPS);         // 4 LOP3 : 4 IMAD.HI
+    if (MODE == 16) asm volatile(IMAD(0) IHI(4) IMAD(1) IHI(5) IMAD(2) IHI(6) IMAD(3) IHI(7) OPS);     // 4 IMAD : 4 IMAD.HI
     if (MODE == 13) asm volatile(LOP(0) IMAD(4) IMAD(5) IMAD(6) LOP(1) IMAD(7) IMAD(4) IMAD(5) OPS);     // 2 ALU : 6 IMAD
   }
   unsigned long long t1 = clock64();
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 + w0 + w1 + w2 + w3;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
-static const int NINSTR[] = {8, 8, 8, 8, 8, 8, 12, 12, 8, 8, 8, 10, 8, 8};
+static const int NINSTR[] = {8, 8, 8, 8, 8, 8, 12, 12, 8, 8, 8, 10, 8, 8, 8, 8, 8};
 template <int MODE>
 void run(const char* name, int sms, int blocks_per_sm, unsigned long long* out, unsigned long long* cyc) {
   const int threads = 256, blocks = sms * blocks_per_sm;
@@ -86,6 +90,9 @@ int main() {
     run<10>("6 IMAD : 2 WIDE", sms, bps, out, cyc);
     run<11>("4 LOP3 : 4 IMAD : 2 WIDE", sms, bps, out, cyc);
     run<12>("2 LOP3 + 2 SHF : 4 IMAD", sms, bps, out, cyc);
+    run<14>("8 IMAD.HI", sms, bps, out, cyc);
+    run<15>("4 LOP3 : 4 IMAD.HI", sms, bps, out, cyc);
+    run<16>("4 IMAD : 4 IMAD.HI", sms, bps, out, cyc);
   }
   return 0;
 }
