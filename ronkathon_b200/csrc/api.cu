@@ -47,6 +47,7 @@ int ronk_ctx_create(ronk_ctx** out, int device, void* stream) {
   ctx->tune.tw_table = env_int("RONK_TW_TABLE", 1);
   ctx->tune.msm_hist = env_int("RONK_MSM_HIST", 1);
   ctx->tune.fast12 = env_int("RONK_FAST12", 1);
+  ctx->tune.msm_split = env_int("RONK_MSM_SPLIT", 0);
   ctx->stream = (cudaStream_t)stream;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return RONK_ECUDA; }

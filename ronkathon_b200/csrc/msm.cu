@@ -149,7 +149,8 @@ __global__ void msm_ytab_kernel(const uint16_t* __restrict__ sq, uint16_t* __res
 
 __global__ void __launch_bounds__(MSM_HIST_THREADS, 1)
 msm_hist_kernel(const u32* __restrict__ points, const uint8_t* __restrict__ scalars, size_t n,
-                const uint16_t* __restrict__ ytab_g, u32* __restrict__ partial, volatile int* host_flag) {
+                const uint16_t* __restrict__ ytab_g, u32* __restrict__ partial, u32* __restrict__ ghist,
+                volatile int* host_flag) {
   extern __shared__ __align__(16) u32 msm_smem[];
   u32* hist = msm_smem;                                      // [MSM_BINS]
   uint16_t* ytab = reinterpret_cast<uint16_t*>(hist + MSM_BINS);  // [MSM_BINS]
@@ -179,7 +180,13 @@ msm_hist_kernel(const u32* __restrict__ points, const uint8_t* __restrict__ scal
       if (__vcmpgeu4(w[u], 0x65656565u)) { bad = true; continue; }  // a coordinate ≥ 101
       const u32 bin = 2u * ((w[u] & 0xFF) + Q101 * ((w[u] >> 8) & 0xFF)) + y_bit((w[u] >> 16) & 0xFF, w[u] >> 24);
       if ((u32)ytab[bin] != (w[u] >> 16)) { bad = true; continue; }  // not on y² = x³ + 3
-      if (s[u]) atomicAdd(&hist[bin], s[u]);                // g1 * 0 = Infinity (curve/mod.rs:163-165)
+      if (!s[u]) continue;                                  // g1 * 0 = Infinity (curve/mod.rs:163-165)
+      // Shared-memory atomics retire about one lane per clock per SM (2^24 terms: 113 k per SM = the kernel's
+      // 58 µs).  RONK_MSM_SPLIT=1 sends every other term to an L2-resident global histogram with a fire-and-forget
+      // RED instead; measured on B200 that is 7× SLOWER (0.41 ms at 2^24 terms: the 20 k hot L2 lines serialise),
+      // so it is off by default and kept only as a recorded negative result.
+      if (ghist && (u & 1)) atomicAdd(&ghist[bin], s[u]);
+      else atomicAdd(&hist[bin], s[u]);
     }
   }
   if (bad) *host_flag = 1;
@@ -189,18 +196,36 @@ msm_hist_kernel(const u32* __restrict__ points, const uint8_t* __restrict__ scal
 }
 
 // CTA tree over one point per thread (len = blockDim.x, a power of two); result in red[0].
+// Five levels inside each warp by shuffles (no barrier), then one warp folds the per-warp sums.
 RONK_DEV void msm_cta_tree(u32* red, u32 t, u32 len, const uint8_t* inv) {
 #if defined(__CUDA_ARCH__)
-  for (u32 half = len / 2; half > 0; half >>= 1) {
-    if (t < half) red[t] = pt_add_t(red[t], red[t + half], inv);
-    __syncthreads();
+  u32 v = red[t];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const u32 o = __shfl_down_sync(0xFFFFFFFFu, v, off);
+    if ((t & 31u) < (u32)off) v = pt_add_t(v, o, inv);
   }
+  __syncthreads();
+  if ((t & 31u) == 0) red[t >> 5] = v;
+  __syncthreads();
+  if (t < 32) {
+    const u32 warps = len >> 5;  // ≤ 32
+    v = (t < warps) ? red[t] : 0xFFFFFFFFu;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const u32 o = __shfl_down_sync(0xFFFFFFFFu, v, off);
+      if (t < (u32)off) v = pt_add_t(v, o, inv);
+    }
+    if (t == 0) red[0] = v;
+  }
+  __syncthreads();
 #endif
 }
 
 __global__ void __launch_bounds__(MSM_FIN_THREADS)
-msm_hist_finish_kernel(const u32* __restrict__ partial, u32 sets, const uint16_t* __restrict__ ytab,
-                       u32* __restrict__ cta_sum, u32* __restrict__ done_counter, volatile u32* host_result) {
+msm_hist_finish_kernel(const u32* __restrict__ partial, u32 sets, u32* __restrict__ ghist,
+                       const uint16_t* __restrict__ ytab, u32* __restrict__ cta_sum, u32* __restrict__ done_counter,
+                       volatile u32* host_result) {
   __shared__ u32 red[MSM_FIN_THREADS];
   __shared__ uint8_t inv[104];
   __shared__ u32 is_last;
@@ -208,8 +233,22 @@ msm_hist_finish_kernel(const u32* __restrict__ partial, u32 sets, const uint16_t
   build_inv_table(inv, t, MSM_FIN_THREADS);
   const u32 bin = blockIdx.x * MSM_FIN_THREADS + t;
   u32 c = 0;
-  if (bin < MSM_BINS)
-    for (u32 g = 0; g < sets; g++) c += partial[(size_t)g * MSM_BINS + bin];
+  if (bin < MSM_BINS) {
+    u32 c0 = 0, c1 = 0, c2 = 0, c3 = 0;  // independent chains: the loads of a column pipeline instead of serialising
+    u32 g = 0;
+    for (; g + 4 <= sets; g += 4) {
+      c0 += partial[(size_t)g * MSM_BINS + bin];
+      c1 += partial[(size_t)(g + 1) * MSM_BINS + bin];
+      c2 += partial[(size_t)(g + 2) * MSM_BINS + bin];
+      c3 += partial[(size_t)(g + 3) * MSM_BINS + bin];
+    }
+    for (; g < sets; g++) c0 += partial[(size_t)g * MSM_BINS + bin];
+    c = c0 + c1 + c2 + c3;
+    if (ghist) {
+      c += ghist[bin];
+      ghist[bin] = 0u;  // self-cleaning: ready for the next call
+    }
+  }
   c %= MSM_EXP;
   __syncthreads();
   u32 acc = PT_INF;
@@ -292,9 +331,9 @@ static int msm_hist_device(ronk_ctx* ctx, const uint8_t* points, size_t n_points
     uint16_t* sq = nullptr;
     RONK_CUDA(ctx, cudaMalloc((void**)&sq, MSM_XS * sizeof(uint16_t)));
     RONK_CUDA(ctx, cudaMalloc((void**)&ctx->msm_ytab, MSM_BINS * sizeof(uint16_t)));
-    RONK_CUDA(ctx, cudaMalloc((void**)&ctx->msm_done, sizeof(u32)));
+    RONK_CUDA(ctx, cudaMalloc((void**)&ctx->msm_done, (1 + MSM_BINS) * sizeof(u32)));  // counter + global histogram
     RONK_CUDA(ctx, cudaMemsetAsync(sq, 0xFF, MSM_XS * sizeof(uint16_t), ctx->stream));
-    RONK_CUDA(ctx, cudaMemsetAsync(ctx->msm_done, 0, sizeof(u32), ctx->stream));
+    RONK_CUDA(ctx, cudaMemsetAsync(ctx->msm_done, 0, (1 + MSM_BINS) * sizeof(u32), ctx->stream));
     {
       LaunchScope ls(ctx, "msm_tables");
       msm_sqrt_table_kernel<<<(MSM_XS + 255) / 256, 256, 0, ctx->stream>>>(sq);
@@ -305,8 +344,8 @@ static int msm_hist_device(ronk_ctx* ctx, const uint8_t* points, size_t n_points
     cudaFree(sq);
   }
   RONK_TRY(ensure_smem_attr(ctx, msm_hist_kernel, (int)kSmem));
-  // one CTA per SM at most; each thread should see ≥ 8 terms before another CTA (and its 82 KB of partial
-  // histogram traffic) is worth it
+  // one CTA per SM at most; each thread should see ≥ 8 terms before another CTA (its table load and its 82 KB of
+  // partial histogram) is worth it (measured: ≥ 32 terms per thread made 2^20 terms slower, 20 vs 12 µs)
   size_t ctas = (n_scalars + (size_t)MSM_HIST_THREADS * 8 - 1) / ((size_t)MSM_HIST_THREADS * 8);
   if (ctas > (size_t)ctx->sm_count) ctas = (size_t)ctx->sm_count;
   if (ctas < 1) ctas = 1;
@@ -316,6 +355,8 @@ static int msm_hist_device(ronk_ctx* ctx, const uint8_t* points, size_t n_points
   RONK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, need));
   u32* partial = (u32*)ctx->ws;
   u32* cta_sum = partial + ctas * MSM_BINS;
+  // the split between shared-memory and L2 atomics pays once the SM's atomic unit is the limiter
+  u32* ghist = (n_scalars >= ((size_t)1 << 22) && ctx->tune.msm_split) ? (u32*)ctx->msm_done + 1 : nullptr;
   volatile u32* host = (volatile u32*)ctx->h_flag;  // mapped pinned: [0] = flag, [1] = result
   host[0] = 0u;
   host[1] = PT_INF;
@@ -324,13 +365,13 @@ static int msm_hist_device(ronk_ctx* ctx, const uint8_t* points, size_t n_points
   {
     LaunchScope ls(ctx, "msm_hist");
     msm_hist_kernel<<<(unsigned)ctas, MSM_HIST_THREADS, kSmem, ctx->stream>>>(
-        (const u32*)points, scalars, n_scalars, (const uint16_t*)ctx->msm_ytab, partial, (volatile int*)host_dev);
+        (const u32*)points, scalars, n_scalars, (const uint16_t*)ctx->msm_ytab, partial, ghist, (volatile int*)host_dev);
   }
   RONK_TRY(check_launch(ctx, "msm_hist_kernel"));
   {
     LaunchScope ls(ctx, "msm_hist_finish");
     msm_hist_finish_kernel<<<fin_ctas, MSM_FIN_THREADS, 0, ctx->stream>>>(
-        partial, (u32)ctas, (const uint16_t*)ctx->msm_ytab, cta_sum, (u32*)ctx->msm_done, (volatile u32*)(host_dev + 1));
+        partial, (u32)ctas, ghist, (const uint16_t*)ctx->msm_ytab, cta_sum, (u32*)ctx->msm_done, (volatile u32*)(host_dev + 1));
   }
   RONK_TRY(check_launch(ctx, "msm_hist_finish_kernel"));
   RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -148,34 +148,28 @@ static int launch_tile_n(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 ti
   return launch_tile_nb<F, MODE, INV, NTHR, MINB, false, false>(ctx, f, A, tiles, name);
 }
 
-// The specialised 4096-point-per-tile kernel (ntt12_kernel.cuh): Goldilocks, unbounded, log_m = 12.
-template <int MODE, bool INV, int LC, int LC2, bool FMUL>
+// The specialised 4096-point-per-tile kernel (ntt12_kernel.cuh): Goldilocks, unbounded, log_m = 12, the default
+// tile shapes (pass 1: 4 columns, pass 2: 2 columns).
+template <int MODE, bool INV, int LC, bool FMUL>
 static int launch12_one(ronk_ctx* ctx, const GoldilocksField& f, const NttTileArgs& A0, u32 tiles, const char* name) {
-  using L = N12<LC>;
+  using L = N12<LC, MODE>;
   NttTileArgs A = A0;
   if (MODE == MODE_PASS1) A.prefetch_dist = (u32)ctx->tune.pf_dist * (u32)ctx->sm_count * (L::NTHR >= 512 ? 1u : 2u);
-  const size_t smem = (size_t)(L::TILE_WORDS + L::TW_WORDS) * sizeof(u64) + 16;
-  RONK_TRY(ensure_smem_attr(ctx, ntt12_kernel<GoldilocksField, MODE, INV, LC, LC2, FMUL>, (int)smem));
+  const size_t smem = (size_t)L::TILE_SLOTS * 16 + (size_t)L::TW_WORDS * sizeof(u64) + 16;
+  RONK_TRY(ensure_smem_attr(ctx, ntt12_kernel<GoldilocksField, MODE, INV, LC, FMUL>, (int)smem));
   {
     LaunchScope ls(ctx, name);
-    ntt12_kernel<GoldilocksField, MODE, INV, LC, LC2, FMUL><<<tiles, L::NTHR, smem, ctx->stream>>>(f, A);
+    ntt12_kernel<GoldilocksField, MODE, INV, LC, FMUL><<<tiles, L::NTHR, smem, ctx->stream>>>(f, A);
   }
   return check_launch(ctx, name);
 }
 template <int MODE, bool INV>
 static int launch12(ronk_ctx* ctx, const GoldilocksField& f, const NttTileArgs& A, u32 tiles, const char* name) {
   if constexpr (MODE == MODE_PASS1) {
-    if (A.log_c2 == 1) return launch12_one<MODE, INV, 2, 1, false>(ctx, f, A, tiles, name);
-    return launch12_one<MODE, INV, 2, 2, false>(ctx, f, A, tiles, name);
+    return launch12_one<MODE, INV, 2, false>(ctx, f, A, tiles, name);
   } else {
-    const bool fmul = !INV && (A.flags & NTT_FLAG_MUL);
-    if (INV && (A.flags & NTT_FLAG_MUL)) return RONK_EUNSUPPORTED;  // never requested: the fused multiply is forward-only
-    if (A.log_c == 1) {
-      if (fmul) return launch12_one<MODE, INV, 1, 1, !INV>(ctx, f, A, tiles, name);
-      return launch12_one<MODE, INV, 1, 1, false>(ctx, f, A, tiles, name);
-    }
-    if (fmul) return launch12_one<MODE, INV, 2, 1, !INV>(ctx, f, A, tiles, name);
-    return launch12_one<MODE, INV, 2, 1, false>(ctx, f, A, tiles, name);
+    if (!INV && (A.flags & NTT_FLAG_MUL)) return launch12_one<MODE, INV, 1, !INV>(ctx, f, A, tiles, name);
+    return launch12_one<MODE, INV, 1, false>(ctx, f, A, tiles, name);
   }
 }
 

@@ -90,39 +90,37 @@ void run_tiles_b(const F& f, const NttTileArgs& A, u64 tiles) {
 // g_fast12: 1 = take it wherever ntt.cu's launch_tile would (the product default), 0 = never.
 int g_fast12 = 1;
 u64 g_fast12_tiles = 0;  // tiles that went through it (so a test can tell the path was really taken)
-template <class F, int MODE, bool INV, int LC, int LC2, bool FMUL>
+template <class F, int MODE, bool INV, int LC, bool FMUL>
 void run_tiles12(const F& f, const NttTileArgs& A, u64 tiles) {
-  using L = N12<LC>;
-  std::vector<u64> smem(L::TILE_WORDS);
+  using L = N12<LC, MODE>;
+  std::vector<u64x2> smem(L::TILE_SLOTS);
   for (u64 tile = 0; tile < tiles; tile++) {
-    for (u32 t = 0; t < L::NTHR; t++) n12_load<MODE, LC>(smem.data(), A, (u32)tile, t);
-    for (u32 t = 0; t < L::NTHR; t++) n12_round<F, INV, LC, 0>(f, smem.data(), A.tw_tile, t);
-    for (u32 t = 0; t < L::NTHR; t++) n12_round<F, INV, LC, 1>(f, smem.data(), A.tw_tile, t);
-    for (u32 t = 0; t < L::NTHR; t++) n12_round<F, INV, LC, 2>(f, smem.data(), A.tw_tile, t);
-    for (u32 t = 0; t < L::NTHR; t++) {
-      if (MODE == MODE_PASS1) n12_store_pass1<F, INV, LC, LC2>(f, smem.data(), A, (u32)tile, t);
-      else n12_store_pass2<F, LC, FMUL>(f, smem.data(), A, (u32)tile, t);
+    for (u32 t = 0; t < L::NTHR; t++) n12_round0_load<F, MODE, INV, LC>(f, smem.data(), A.tw_tile, A, (u32)tile, t);
+    for (u32 t = 0; t < L::NTHR; t++) n12_round<F, MODE, INV, LC, 1>(f, smem.data(), A.tw_tile, t);
+    if constexpr (MODE == MODE_PASS1) {
+      for (u32 t = 0; t < L::NTHR; t++) n12_round<F, MODE, INV, LC, 2>(f, smem.data(), A.tw_tile, t);
+      for (u32 t = 0; t < L::NTHR; t++) n12_store_pass1<F, LC>(f, smem.data(), A, (u32)tile, t);
+    } else {
+      // warp-local hand-over from round 1 to round 2: run it warp by warp to mirror the kernel's __syncwarp()
+      for (u32 t = 0; t < L::NTHR; t++) n12_round2_store_pass2<F, INV, LC, FMUL>(f, smem.data(), A, (u32)tile, t);
     }
   }
   g_fast12_tiles += tiles;
 }
 template <class F, int MODE, bool INV>
 bool try_tiles12(const F& f, const NttTileArgs& A, u64 tiles) {  // same dispatch as launch12() in ntt.cu
-  if (!g_fast12 || MODE == MODE_SINGLE || !ntt12_applicable(A, MODE) || (INV && (A.flags & NTT_FLAG_MUL))) return false;
-  if (MODE == MODE_PASS1) {
-    if (A.log_c2 == 1) run_tiles12<F, MODE, INV, 2, 1, false>(f, A, tiles);
-    else run_tiles12<F, MODE, INV, 2, 2, false>(f, A, tiles);
+  if constexpr (MODE == MODE_SINGLE) {
+    return false;
+  } else {
+    if (!g_fast12 || !ntt12_applicable(A, MODE) || (INV && (A.flags & NTT_FLAG_MUL))) return false;
+    if constexpr (MODE == MODE_PASS1) {
+      run_tiles12<F, MODE, INV, 2, false>(f, A, tiles);
+    } else {
+      if (!INV && (A.flags & NTT_FLAG_MUL)) run_tiles12<F, MODE, INV, 1, !INV>(f, A, tiles);
+      else run_tiles12<F, MODE, INV, 1, false>(f, A, tiles);
+    }
     return true;
   }
-  const bool fmul = !INV && (A.flags & NTT_FLAG_MUL);
-  if (A.log_c == 1) {
-    if (fmul) run_tiles12<F, MODE, INV, 1, 1, true>(f, A, tiles);
-    else run_tiles12<F, MODE, INV, 1, 1, false>(f, A, tiles);
-  } else {
-    if (fmul) run_tiles12<F, MODE, INV, 2, 1, true>(f, A, tiles);
-    else run_tiles12<F, MODE, INV, 2, 1, false>(f, A, tiles);
-  }
-  return true;
 }
 
 // src == nullptr: in place; otherwise the bounded out-of-place form of run_ntt() in ntt.cu (batch 1)
@@ -201,56 +199,49 @@ int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 l
 }  // namespace
 
 
-// Bank-conflict audit of the additive layout of ntt12_kernel.cuh: worst multiplicity of an 8-byte bank within a
-// half-warp over every access of every phase (load, three rounds, both store forms); 1 = conflict-free.
-// Also checks that word() is injective on the tile and stays inside TILE_WORDS (returns -1 otherwise).
-template <int LC, int LC2>
-static int layout12_worst(int mode) {
-  using L = N12<LC>;
-  std::vector<int> seen(L::TILE_WORDS, 0);
-  for (u32 e = 0; e < L::T; e++) {
-    if (L::word(e) >= L::TILE_WORDS || seen[L::word(e)]++) return -1;
-  }
+// Bank-conflict audit of the additive layout of ntt12_kernel.cuh: worst multiplicity of a bank within one
+// shared-memory transaction over every access of every phase; 1 = conflict-free.  128-bit accesses are served 8
+// lanes at a time against eight 16-byte banks (slot mod 8); the 64-bit reads of the pass-1 store 16 lanes at a
+// time against sixteen 8-byte banks.  Also checks that word() is injective and stays inside TILE_SLOTS (-1 if not).
+template <int LC, int MODE>
+static int layout12_worst() {
+  using L = N12<LC, MODE>;
+  std::vector<int> seen(L::TILE_SLOTS, 0);
+  for (u32 e = 0; e < L::PAIRS; e++)
+    if (L::word(e) >= L::TILE_SLOTS || seen[L::word(e)]++) return -1;
   int worst = 1;
-  auto account = [&](const std::vector<u32>& words) {  // one access instruction of one half-warp
-    int cnt[16] = {0};
-    for (u32 w : words) cnt[w & 15]++;
-    for (int k = 0; k < 16; k++) worst = cnt[k] > worst ? cnt[k] : worst;
+  auto account = [&](const std::vector<u32>& banks, int nb) {
+    std::vector<int> cnt(nb, 0);
+    for (u32 w : banks) cnt[w % nb]++;
+    for (int k = 0; k < nb; k++) worst = cnt[k] > worst ? cnt[k] : worst;
   };
-  for (u32 hw = 0; hw < L::NTHR / 16; hw++) {
-    for (u32 j = 0; j < 32; j++) {  // load: e = tid + j·NTHR
-      std::vector<u32> w;
-      for (u32 l = 0; l < 16; l++) w.push_back(L::word(hw * 16 + l + (j << L::KK)));
-      account(w);
-    }
+  for (u32 q8 = 0; q8 < L::NTHR / 8; q8++) {
     for (int R = 0; R < 3; R++) {
-      const u32 wb = LC + 8 - 4 * R;
-      for (u32 g = 0; g < 2; g++)
-        for (u32 q = 0; q < 16; q++) {
+      const u32 wb = L::LP + 8 - 4 * R;
+      for (u32 q = 0; q < 16; q++) {
+        std::vector<u32> w;
+        for (u32 l = 0; l < 8; l++) {
+          const u32 t = q8 * 8 + l;
+          const u32 e0 = ((t >> wb) << (wb + 4)) | (t & ((1u << wb) - 1u));
+          w.push_back(L::word(e0 | (q << wb)));
+        }
+        account(w, 8);
+      }
+    }
+  }
+  if (MODE == MODE_PASS1) {  // 64-bit reads: 16 lanes, bank = 2·slot + half
+    for (u32 hw = 0; hw < L::NTHR / 16; hw++)
+      for (u32 j = 0; j < 16; j++)
+        for (u32 h = 0; h < 2; h++) {
           std::vector<u32> w;
           for (u32 l = 0; l < 16; l++) {
-            const u32 t = hw * 16 + l + g * L::NTHR;
-            const u32 e0 = ((t >> wb) << (wb + 4)) | (t & ((1u << wb) - 1u));
-            w.push_back(L::word(e0 | (q << wb)));
+            const u32 g = hw * 16 + l + (j << L::KK);
+            const u32 c = g & (L::C - 1u), blk = g >> LC;
+            const u32 e = (bitrev12c(2 * blk + h) << L::LP) | (c >> 1);
+            w.push_back(2 * L::word(e) + (c & 1u));
           }
-          account(w);
+          account(w, 16);
         }
-    }
-    for (u32 j = 0; j < 32; j++) {  // store: tile index of output element g = tid + j·NTHR
-      std::vector<u32> w;
-      for (u32 l = 0; l < 16; l++) {
-        const u32 g = hw * 16 + l + (j << L::KK);
-        u32 e;
-        if (mode == MODE_PASS2) e = (bitrev12c(g >> LC) << LC) | (g & (L::C - 1u));
-        else {
-          const u32 cl = LC + LC2, rem = g & ((1u << cl) - 1u);
-          const u32 k1 = ((g >> cl) << LC2) | (rem & ((1u << LC2) - 1u));
-          e = (bitrev12c(k1) << LC) | (rem >> LC2);
-        }
-        w.push_back(L::word(e));
-      }
-      account(w);
-    }
   }
   return worst;
 }
@@ -276,11 +267,10 @@ void emu_set_fast12(int on) { g_fast12 = on; }
 uint64_t emu_fast12_tiles(void) { return g_fast12_tiles; }
 
 void emu_set_tw_table(int on) { g_tw_table = on; }
-int emu_layout12_worst_conflict(int mode, int lc, int lc2) {
-  if (mode == MODE_PASS1 && lc == 2 && lc2 == 1) return layout12_worst<2, 1>(mode);
-  if (mode == MODE_PASS1 && lc == 2 && lc2 == 2) return layout12_worst<2, 2>(mode);
-  if (mode == MODE_PASS2 && lc == 1) return layout12_worst<1, 1>(mode);
-  if (mode == MODE_PASS2 && lc == 2) return layout12_worst<2, 1>(mode);
+int emu_layout12_worst_conflict(int mode, int lc) {
+  if (mode == MODE_PASS1 && lc == 2) return layout12_worst<2, MODE_PASS1>();
+  if (mode == MODE_PASS2 && lc == 1) return layout12_worst<1, MODE_PASS2>();
+  if (mode == MODE_PASS2 && lc == 2) return layout12_worst<2, MODE_PASS2>();
   return -2;
 }
 

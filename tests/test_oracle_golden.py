@@ -258,3 +258,17 @@ def test_next_rows_against_independent_vectors():
     assert [int(v) for v in oracle.rs_decode(GL, xs, ys, 5)] == d["msg"]
     d = g["interpolate_12_seed71_seed72"]
     assert [int(v) for v in oracle.rs_decode(GL, d["xs"], d["ys"], 12)] == d["coeffs"]
+
+
+def test_kat_provenance_is_mechanical():
+    """tests/golden/extract_reference_kats.py parses the reference's rstest tables and locates every other vector of
+    reference_kats.json in the cited Rust source.  Needs /root/reference (absent on the GPU box → skipped)."""
+    import json
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("reference sources not present on this box")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "extract_reference_kats.py")
+    out = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert json.loads(out.stdout)["located"] >= 114

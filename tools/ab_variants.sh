@@ -25,7 +25,7 @@ case "$1" in
   run)
     shift
     for name in "$@"; do
-      RONK_LIB_PATH="$ROOT/variants/libronk_$name.so" python "$ROOT/bench.py" --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null |
+      RONK_LIB_PATH="$ROOT/variants/libronk_$name.so" python "$ROOT/bench.py" --steps 20 --warmup 5 --no-cpu-baseline --no-extras 2>/dev/null |
         python -c "
 import json, sys
 d = json.loads(sys.stdin.read())

@@ -1,14 +1,15 @@
 #!/usr/bin/env python3
-"""Multi-GPU validation + timing (run under torchrun, one rank per GPU, NCCL over NVLink):
+"""Multi-GPU parity checks through the C ABI's ronk_dist_* entry points (run under torchrun, one rank per GPU):
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
       --master-port 29511 tools/multi_gpu_check.py
 
-Checks, bit-exactly against the oracle: (1) one 2^20-point transform spread over the N GPUs
-(local NTT → twiddle column → ONE all-to-all → cross-rank butterflies), (2) BASELINE config 5's
-batched transforms sharded by contiguous batch ranges (no collective), (3) kzg::commit with
-index-range shards + 68-byte bucket all-gather.  Then times config 5 (4096 × 2^16 over N GPUs) and
-the distributed 2^24 transform with CUDA events, max over ranks.  Prints one JSON line on rank 0."""
+Bit-exact against the oracle: the distributed transform (both exchange flavours) over a sweep of sizes and batch
+counts — including local transforms that are single-tile, two-pass and 4096-point-per-tile — with Goldilocks and
+with a generic-modulus (Montgomery) field; contiguous batch shards with an uneven split; kzg::commit over
+index-range shards (incl. empty shards and a rejected term seen by every rank); two contexts alternating in one
+process (device binding).  bench.py --gpus N carries the full-size timings (`multi` block).
+Prints one JSON line on rank 0."""
 import json
 import os
 import sys
@@ -19,10 +20,10 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import oracle  # noqa: E402
-from ronkathon_b200 import Context, ops  # noqa: E402
+from bench import msm_terms  # noqa: E402
+from ronkathon_b200 import Context, RonkPanic, ops  # noqa: E402
 from ronkathon_b200 import dist as rd  # noqa: E402
 
 GL = oracle.GOLDILOCKS
@@ -34,84 +35,103 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ctx = Context(local, torch.cuda.current_stream().cuda_stream)
-    lo = rd.LocalOps(ctx)
+    dctx = rd.DistContext(ctx)
     res = {"n_gpus": world}
+    lg_w = world.bit_length() - 1
 
-    # (1) one large transform across the group
-    lg = 20
-    a = oracle.splitmix(GL, 42, 1 << lg)
-    out = rd.ntt_distributed(lo, ops.to_device(a[rank::world].copy(), dev), lg)
-    full = ops.to_host(rd.gather_distributed_output(out, lg))
-    res["dist_ntt_2_20_bit_exact"] = bool(np.array_equal(full, oracle.ntt_fast(GL, a)))
+    def gather_host(t):
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t.contiguous())
+        return [ops.to_host(p) for p in parts]
 
-    # (1b) the same transform with the exchange fused into the final kernel (P2P loads over NVLink)
-    fused = rd.FusedDistributedNTT(ctx, lg)
-    out_f = fused.run(ops.to_device(a[rank::world].copy(), dev))
-    full_f = ops.to_host(rd.gather_distributed_output(out_f, lg))
-    res["fused_dist_ntt_2_20_bit_exact"] = bool(np.array_equal(full_f, oracle.ntt_fast(GL, a)))
-    fused.close()
+    def check_dist(p, g, log_n, batch, flavour):
+        n, m = 1 << log_n, (1 << log_n) // world
+        blk = m // world
+        full = [oracle.splitmix(p, 900 + 31 * b + log_n, n) for b in range(batch)]   # same on every rank
+        loc = ops.to_device(np.concatenate([a[rank::world] for a in full]), dev)
+        dctx.ntt_dist(loc, log_n, batch, flavour, p=p, g=g)
+        ctx.sync()
+        outs = gather_host(loc)
+        ok = True
+        for b in range(batch):
+            X = np.empty(n, dtype=np.uint64)
+            for s in range(world):
+                o = outs[s][b * m:(b + 1) * m].reshape(world, blk)
+                for q in range(world):
+                    X[s * blk + m * q: s * blk + m * q + blk] = o[q]
+            ok = ok and bool(np.array_equal(X, oracle.ntt_fast(p, full[b], g=g)))
+        return ok
 
-    # (2) config-5 shape, reduced batch for the oracle check: 64 × 2^16
-    batch, lgb = 64, 16
-    data = oracle.splitmix(GL, 7, batch << lgb)
-    b0, b1 = rd.shard_range(batch, rank, world)
-    shard = ops.to_device(data[b0 << lgb:b1 << lgb].copy(), dev)
-    rd.ntt_batch_sharded(lo, shard, lgb)
+    sweep = {}
+    for flavour, fname in ((rd.DIST_NCCL, "nccl"), (rd.DIST_FUSED, "fused")):
+        for log_n in sorted({max(2 * lg_w, 4), 8, 12, 15, 16, 20, 12 + lg_w + 12 if 24 + lg_w <= 26 else 24}):
+            if log_n < 2 * lg_w:
+                continue
+            for batch in (1, 3):
+                if log_n >= 24 and batch > 1:
+                    continue
+                sweep[f"{fname}_2^{log_n}_x{batch}"] = check_dist(GL, 7, log_n, batch, flavour)
+        # generic modulus through the Montgomery policy: p = 2^32·k + 1 style prime with 2-adicity 32 → use 0xFFFFFFFF00000001
+        # with a non-default generator (routes to MontField), and a 31-bit NTT prime
+        sweep[f"{fname}_mont_gl_g5_2^12"] = check_dist(GL, pow(7, 5, GL), 12, 2, flavour)
+        sweep[f"{fname}_mont_p2013265921_2^10"] = check_dist(2013265921, 31, 10, 2, flavour)   # 15·2^27 + 1
+    res["dist_ntt"] = sweep
+    res["dist_ntt_all_bit_exact"] = all(sweep.values())
+
+    # contiguous batch shards, uneven split (world does not divide 13 for world ≥ 2 except …)
+    total, lgb = 13, 14
+    data = oracle.splitmix(GL, 7, total << lgb)
+    lo, hi = dctx.shard_range(total)
+    shard = ops.to_device(data[lo << lgb:hi << lgb].copy() if hi > lo else np.zeros(0, dtype=np.uint64), dev)
+    got_lo, got_hi = dctx.ntt_batch_sharded(shard if hi > lo else torch.zeros(1, dtype=torch.int64, device=dev), lgb, total)
     ctx.sync()
-    got = ops.to_host(shard)
-    ok = True
-    for b in {b0, (b0 + b1) // 2, b1 - 1}:
-        ok &= bool(np.array_equal(got[(b - b0) << lgb:(b - b0 + 1) << lgb], oracle.ntt_fast(GL, data[b << lgb:(b + 1) << lgb])))
-    res["batched_sharded_bit_exact"] = ok
+    ok = (got_lo, got_hi) == (lo, hi)
+    for b in range(lo, hi):
+        ok = ok and bool(np.array_equal(ops.to_host(shard)[(b - lo) << lgb:(b - lo + 1) << lgb],
+                                        oracle.ntt_fast(GL, data[b << lgb:(b + 1) << lgb])))
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(ok))
+    res["batch_sharded_uneven_bit_exact"] = all(flags)
 
-    # (3) MSM 2^20 terms, index-range shards
-    from gpu_util import msm_inputs
-    n = 1 << 20
-    pts, sc = msm_inputs(n)
-    i0, i1 = rd.shard_range(n, rank, world)
-    got = rd.msm_distributed(lo, torch.from_numpy(pts[i0:i1].copy()).to(dev), torch.from_numpy(sc[i0:i1].copy()).to(dev))
-    if rank == 0:
-        res["msm_2_20_bit_exact"] = got == oracle.commit(sc, pts, fast=True)
+    # kzg::commit over index-range shards: 2^16 + 5 terms, a 3-term input (empty shards), a rejected term
+    commits = {}
+    for n in ((1 << 16) + 5, 3):
+        pts, sc = msm_terms(n)
+        i0, i1 = dctx.shard_range(n)
+        P = torch.from_numpy(pts[i0:i1].copy()).to(dev) if i1 > i0 else torch.zeros((1, 4), dtype=torch.uint8, device=dev)
+        S = torch.from_numpy(sc[i0:i1].copy()).to(dev) if i1 > i0 else torch.zeros(0, dtype=torch.uint8, device=dev)
+        got = dctx.msm(P, S)
+        commits[str(n)] = bool(got == oracle.commit(sc, pts, fast=True))
+    pts, sc = msm_terms(1 << 12)
+    sc[len(sc) - 1] = 17            # not an F17 residue, lands in the last rank's shard
+    i0, i1 = dctx.shard_range(len(sc))
+    try:
+        dctx.msm(torch.from_numpy(pts[i0:i1].copy()).to(dev), torch.from_numpy(sc[i0:i1].copy()).to(dev))
+        rejected = False
+    except RonkPanic:
+        rejected = True
+    flags = [None] * world
+    dist.all_gather_object(flags, rejected)
+    commits["rejected_on_every_rank"] = all(flags)
+    res["commit_sharded"] = commits
 
-    def timed(fn, iters=10, warm=3):
-        for _ in range(warm):
-            fn()
-        dist.barrier(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        dist.barrier(); torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # config 5 at full size: 4096 × 2^16, strong scaling (total fixed)
-    total_batch = 4096
-    b0, b1 = rd.shard_range(total_batch, rank, world)
-    buf = ops.splitmix_fill(ctx, (b1 - b0) << 16, 100 + rank, GL, dev)
-    ms = timed(lambda: rd.ntt_batch_sharded(lo, buf, 16))
-    res["config5_ms"] = ms
-    res["config5_field_muls_per_s"] = total_batch * (1 << 15) * 16 / (ms * 1e-3)
-
-    # one 2^24 transform across the group (capacity mode)
-    lg = 24
-    locbuf = ops.splitmix_fill(ctx, (1 << lg) // world, 5 + rank, GL, dev)
-    scratch = locbuf.clone()
-
-    def one():
-        scratch.copy_(locbuf)
-        rd.ntt_distributed(lo, scratch, lg)
-    res["dist_ntt_2_24_ms"] = timed(one, iters=5)
-    fused24 = rd.FusedDistributedNTT(ctx, lg)
-    outbuf = torch.empty_like(locbuf)
-    res["fused_dist_ntt_2_24_ms"] = timed(lambda: fused24.run(locbuf, outbuf), iters=5)
-    fused24.close()
-
-    # MSM 2^20 timing
-    P, S = torch.from_numpy(pts[i0:i1].copy()).to(dev), torch.from_numpy(sc[i0:i1].copy()).to(dev)
-    res["msm_2_20_ms"] = timed(lambda: rd.msm_distributed(lo, P, S), iters=5)
+    # two contexts for two devices alternating in ONE process (rank 0 only; needs ≥ 2 visible GPUs)
+    if rank == 0 and torch.cuda.device_count() >= 2:
+        other = Context(1, 0)
+        a = oracle.splitmix(GL, 3, 1 << 16)
+        d0 = ops.to_device(a, dev)
+        d1 = ops.to_device(a, torch.device("cuda", 1))
+        for _ in range(3):
+            ops.ntt_(ctx, d0, 16)
+            ops.ntt_(other, d1, 16)
+            ops.ntt_(ctx, d0, 16, inverse=True)
+            ops.ntt_(other, d1, 16, inverse=True)
+        ctx.sync(); other.sync()
+        res["two_contexts_one_process"] = bool(np.array_equal(ops.to_host(d0), a) and np.array_equal(ops.to_host(d1), a)
+                                               and torch.cuda.current_device() == local)
+        other.close()
+    dist.barrier()
+    dctx.close()
     if rank == 0:
         print(json.dumps(res), flush=True)
     dist.destroy_process_group()
