@@ -321,4 +321,39 @@ struct Message {  // reed_solomon.rs:13-17
 
 }  // namespace codes
 
+// ---------------------------------------------------------------------------------------------
+// multi-GPU modes: one Context per GPU; the library owns the NCCL communicator.  The host only
+// carries the 128-byte id from rank 0 to the other ranks (MPI_Bcast, a TCP store …).
+// ---------------------------------------------------------------------------------------------
+namespace dist {
+
+inline std::array<uint8_t, RONK_NCCL_UNIQUE_ID_BYTES> unique_id() {  // rank 0
+  std::array<uint8_t, RONK_NCCL_UNIQUE_ID_BYTES> id{};
+  const int rc = ronk_dist_unique_id(id.data());
+  if (rc != RONK_OK) throw Error(rc, "ronk_dist_unique_id: libnccl.so.2 not available");
+  return id;
+}
+inline void init(Context& c, const std::array<uint8_t, RONK_NCCL_UNIQUE_ID_BYTES>& id, int rank, int world) {
+  c.check(ronk_dist_init(c.get(), id.data(), rank, world));
+}
+inline void finalize(Context& c) { c.check(ronk_dist_finalize(c.get())); }
+// device pointers, as in the C ABI
+inline std::pair<uint64_t, uint64_t> ntt_batch_sharded(Context& c, uint64_t p, uint64_t g, uint64_t* shard, uint32_t log_n,
+                                                       uint64_t total_batch, bool inverse = false) {
+  uint64_t lo = 0, hi = 0;
+  c.check(ronk_ntt_u64_batch_sharded(c.get(), p, g, shard, log_n, total_batch, inverse ? 1 : 0, &lo, &hi));
+  return {lo, hi};
+}
+inline void ntt(Context& c, uint64_t p, uint64_t g, uint64_t* local, uint32_t log_n, uint32_t batch = 1,
+                int flavour = RONK_DIST_FUSED) {
+  c.check(ronk_ntt_u64_dist(c.get(), p, g, local, log_n, batch, flavour));
+}
+inline AffinePoint commit(Context& c, const uint8_t* points, const uint8_t* scalars, size_t n) {
+  AffinePoint out;
+  c.check(ronk_msm_pluto_ext_dist(c.get(), points, n, scalars, n, out.raw.data()));
+  return out;
+}
+
+}  // namespace dist
+
 }  // namespace ronk

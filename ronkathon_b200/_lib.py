@@ -137,6 +137,7 @@ class Context:
             self._h = None
             raise RonkError(rc, "ronk_ctx_create failed — a B200 (sm_100) GPU is required; no CPU fallback exists")
         self.device = device
+        self.stream = int(stream) if stream else 0   # raw cudaStream_t the context enqueues on (0 = legacy default)
 
     def check(self, rc: int):
         if rc == OK:
@@ -152,6 +153,7 @@ class Context:
 
     def set_stream(self, stream: int):
         self.call("ronk_ctx_set_stream", vp(stream) if stream else None)
+        self.stream = int(stream) if stream else 0
 
     @property
     def launches(self) -> int:

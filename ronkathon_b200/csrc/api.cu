@@ -40,13 +40,14 @@ int ronk_ctx_create(ronk_ctx** out, int device, void* stream) {
     return s ? atoi(s) : dflt;
   };
   ctx->tune.pf_dist = env_int("RONK_PF_DIST", 1);
+  ctx->tune.pf_dist2 = env_int("RONK_PF_DIST2", 1);
   ctx->tune.single_tile_log = env_int("RONK_SINGLE_TILE_LOG", 12);
   ctx->tune.tile1 = env_int("RONK_TILE1", 14);
   ctx->tune.tile2 = env_int("RONK_TILE2", 13);
   ctx->tune.tile_adapt = env_int("RONK_TILE_ADAPT", 1);
-  ctx->tune.tw_table = env_int("RONK_TW_TABLE", 1);
+  ctx->tune.fast12 = env_int("RONK_FAST12", 0);
+  ctx->tune.tw_table = env_int("RONK_TW_TABLE", ctx->tune.fast12 ? 1 : 0);  // the specialised pass 1 reads the table
   ctx->tune.msm_hist = env_int("RONK_MSM_HIST", 1);
-  ctx->tune.fast12 = env_int("RONK_FAST12", 1);
   ctx->tune.msm_split = env_int("RONK_MSM_SPLIT", 0);
   ctx->stream = (cudaStream_t)stream;
   cudaDeviceProp prop;

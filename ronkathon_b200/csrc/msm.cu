@@ -234,16 +234,19 @@ msm_hist_finish_kernel(const u32* __restrict__ partial, u32 sets, u32* __restric
   const u32 bin = blockIdx.x * MSM_FIN_THREADS + t;
   u32 c = 0;
   if (bin < MSM_BINS) {
-    u32 c0 = 0, c1 = 0, c2 = 0, c3 = 0;  // independent chains: the loads of a column pipeline instead of serialising
+    // 16 loads of the column in flight per step: the column sum is a chain of L2 latencies otherwise
+    // (148 partial histograms: 10 steps instead of 148)
+    u32 acc16[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc16[k] = 0u;
     u32 g = 0;
-    for (; g + 4 <= sets; g += 4) {
-      c0 += partial[(size_t)g * MSM_BINS + bin];
-      c1 += partial[(size_t)(g + 1) * MSM_BINS + bin];
-      c2 += partial[(size_t)(g + 2) * MSM_BINS + bin];
-      c3 += partial[(size_t)(g + 3) * MSM_BINS + bin];
+    for (; g + 16 <= sets; g += 16) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) acc16[k] += partial[(size_t)(g + k) * MSM_BINS + bin];
     }
-    for (; g < sets; g++) c0 += partial[(size_t)g * MSM_BINS + bin];
-    c = c0 + c1 + c2 + c3;
+    for (; g < sets; g++) acc16[0] += partial[(size_t)g * MSM_BINS + bin];
+#pragma unroll
+    for (int k = 0; k < 16; k++) c += acc16[k];
     if (ghist) {
       c += ghist[bin];
       ghist[bin] = 0u;  // self-cleaning: ready for the next call

@@ -155,6 +155,7 @@ static int launch12_one(ronk_ctx* ctx, const GoldilocksField& f, const NttTileAr
   using L = N12<LC, MODE>;
   NttTileArgs A = A0;
   if (MODE == MODE_PASS1) A.prefetch_dist = (u32)ctx->tune.pf_dist * (u32)ctx->sm_count * (L::NTHR >= 512 ? 1u : 2u);
+  if (MODE == MODE_PASS2) A.prefetch_dist = (u32)ctx->tune.pf_dist2 * (u32)ctx->sm_count * (L::NTHR >= 512 ? 1u : 2u);
   const size_t smem = (size_t)L::TILE_SLOTS * 16 + (size_t)L::TW_WORDS * sizeof(u64) + 16;
   RONK_TRY(ensure_smem_attr(ctx, ntt12_kernel<GoldilocksField, MODE, INV, LC, FMUL>, (int)smem));
   {

@@ -61,7 +61,8 @@ RONK_DEV void st_pair(u64* p, u64x2 v) { *reinterpret_cast<u64x2*>(p) = v; }
 // 16 rows × 32 B in pass 1), transforms them and only then writes the tile: no separate load phase, one
 // shared-memory round trip and one CTA barrier less per tile.
 template <class F, int MODE, bool INV, int LC>
-RONK_DEV void n12_round0_load(const F& f, u64x2* smem, const u64* tw, const NttTileArgs& A, u32 tile, u32 tid) {
+RONK_DEV void n12_round0_load(const F& f, u64x2* smem, const u64* tw, const NttTileArgs& A, u32 tile, u32 tid,
+                              u64* tw_barrier = nullptr) {
   using L = N12<LC, MODE>;
   constexpr int WB = L::LP + 8;
   const u32 b = tile / A.tiles_per_batch, sub = tile - b * A.tiles_per_batch;
@@ -83,6 +84,9 @@ RONK_DEV void n12_round0_load(const F& f, u64x2* smem, const u64* tw, const NttT
   }
   radix_network<4, INV>(f, xa);
   radix_network<4, INV>(f, xb);
+#if defined(__CUDA_ARCH__)
+  if (tw_barrier) mbar_wait(tw_barrier, 0);  // the twiddle table (TMA bulk copy) landed while the tile was being fetched
+#endif
   const u32 i2 = (tid >> L::LP) & 255u;
   const u64* row = tw + i2 * TW_ROW;
 #pragma unroll
@@ -226,10 +230,18 @@ __global__ void __launch_bounds__(N12<LC, MODE>::NTHR, N12<LC, MODE>::NTHR >= 51
     mbar_expect_tx(bar, L::TW_WORDS * 8u);
     tma_bulk_g2s(tw, A.tw_tile, L::TW_WORDS * 8u, bar);  // lands while the tile itself is being loaded
   }
+  __syncthreads();  // the mbarrier is initialised before anyone waits on it
   if (MODE == MODE_PASS1 && A.prefetch_dist && tile + A.prefetch_dist < gridDim.x)
     ntt_prefetch_pass1(A, tile + A.prefetch_dist, tid, L::NTHR);
-  mbar_wait(bar, 0);
-  n12_round0_load<F, MODE, INV, LC>(f, smem, tw, A, tile, tid);
+  if (MODE == MODE_PASS2 && A.prefetch_dist && tile + A.prefetch_dist < gridDim.x && (tid & 7u) == 0) {
+    // round 0 consumes its loads at once, so their latency is exposed: ask L2 for the tile of the CTA that will
+    // follow this one on the SM (one 128-byte line per 8 threads and step)
+    const u32 nt = tile + A.prefetch_dist, nb = nt / A.tiles_per_batch, nsub = nt - nb * A.tiles_per_batch;
+    const u64* p = A.src + ((u64)nb << A.log_n) + ((u64)nsub << (L::TLP + 1)) + 2u * tid;
+#pragma unroll
+    for (int q = 0; q < 16; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + ((u64)q << (L::LP + 9))));
+  }
+  n12_round0_load<F, MODE, INV, LC>(f, smem, tw, A, tile, tid, bar);
   __syncthreads();
   n12_round<F, MODE, INV, LC, 1>(f, smem, tw, tid);
   // rounds 1 and 2 of one i_hi digit are done by the same 2^(LP+4) consecutive threads — half a warp or a warp —

@@ -42,13 +42,15 @@ struct NttPlan {
 
 // Tuning switches, read from the environment ONCE at ronk_ctx_create (never on the launch path).
 struct ronk_tune {
+  int pf_dist2 = 1;         // RONK_PF_DIST2: the same for pass 2 of the specialised kernel (round 0 fed from HBM)
   int pf_dist = 1;          // RONK_PF_DIST: pass-1 L2 prefetch distance in waves of co-resident CTAs (0 = off)
   int single_tile_log = 12; // RONK_SINGLE_TILE_LOG: preferred tile size when several small transforms share a tile
   int tile1 = 14, tile2 = 13, tile_adapt = 1;  // RONK_TILE1 / RONK_TILE2 / RONK_TILE_ADAPT
-  int fast12 = 1;           // RONK_FAST12: the specialised 4096-point-per-tile kernel (ntt12_kernel.cuh) where it applies
+  int fast12 = 0;           // RONK_FAST12: the specialised 4096-point-per-tile kernel (ntt12_kernel.cuh) where it applies — opt-in:
+                            // 20 % fewer instructions but slower on B200 (0.392 vs 0.379 ms); needs RONK_TW_TABLE=1 for pass 1
   int msm_split = 0;        // RONK_MSM_SPLIT: ≥ 2^22 terms: every other term to an L2-resident histogram (global RED)
   int msm_hist = 1;         // RONK_MSM_HIST: kzg::commit through the point-indexed histogram (1) or the bucket kernels (0)
-  int tw_table = 1;         // RONK_TW_TABLE: inter-pass twiddles from an n-word table (1) or stepped w ← w·ρ (0)
+  int tw_table = 0;         // RONK_TW_TABLE: inter-pass twiddles from an n-word table (1) or stepped w ← w·ρ (0)
 };
 
 struct ronk_ctx {

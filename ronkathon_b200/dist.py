@@ -36,6 +36,14 @@ class LocalOps:
 
     def __init__(self, ctx, p: int = GOLDILOCKS, g: int = 7):
         self.ctx, self.p, self.g = ctx, p, g
+        # torch's collectives and caching allocator are ordered on torch's CURRENT stream, the kernels on the
+        # context's: the algorithms below interleave the two without events, which is only correct when they are
+        # the same stream.  Refuse anything else instead of racing silently.
+        if torch.cuda.is_available() and hasattr(ctx, "stream"):
+            cur = torch.cuda.current_stream().cuda_stream
+            if int(ctx.stream) != int(cur):
+                raise ValueError("LocalOps needs a Context created on torch's current stream "
+                                 f"(context stream {ctx.stream:#x}, torch current stream {cur:#x})")
 
     def root_of_unity(self, n: int) -> int:
         import ctypes as C

@@ -93,6 +93,41 @@ int main() {
     codes::Message<G64> mg(big);
     CHECK(codes::Message<G64>::decode(mg.encode(512), 300).data == big);   // power of two: the NTT path
   }
+  {  // multi-GPU entry points with a world of one (the N > 1 paths run under torchrun: tools/multi_gpu_check.py)
+    Context& c = Context::global();
+    dist::init(c, dist::unique_id(), 0, 1);
+    int r = -1, w = -1;
+    CHECK(ronk_dist_rank(c.get(), &r, &w) == RONK_OK && r == 0 && w == 1);
+    uint64_t lo = 9, hi = 9;
+    CHECK(ronk_dist_shard_range(13, 2, 4, &lo, &hi) == RONK_OK && lo == 7 && hi == 10);
+    const uint64_t P = RONK_GOLDILOCKS;
+    std::vector<uint64_t> h(1 << 10), ref;
+    for (size_t i = 0; i < h.size(); i++) h[i] = (i * 2654435761ULL + 12345) % P;
+    ref = h;
+    c.check(ronk_ntt_u64_host(c.get(), P, 7, ref.data(), 10, 1, 0));
+    void* d = nullptr;
+    c.check(ronk_dev_alloc(c.get(), &d, h.size() * 8));
+    c.check(ronk_memcpy_h2d(c.get(), d, h.data(), h.size() * 8));
+    dist::ntt(c, P, 7, (uint64_t*)d, 10, 1, RONK_DIST_NCCL);          // G = 1: the whole transform is local
+    std::vector<uint64_t> got(h.size());
+    c.check(ronk_memcpy_d2h(c.get(), got.data(), d, h.size() * 8));
+    CHECK(got == ref);
+    c.check(ronk_memcpy_h2d(c.get(), d, h.data(), h.size() * 8));
+    auto range = dist::ntt_batch_sharded(c, P, 7, (uint64_t*)d, 8, 4);   // 4 transforms of 256 points, all ours
+    CHECK(range.first == 0 && range.second == 4);
+    auto srs = kzg::setup();
+    std::vector<uint8_t> pts, sc = {7, 16, 1, 11, 1};
+    for (size_t i = 0; i < sc.size(); i++) pts.insert(pts.end(), srs.first[i].raw.begin(), srs.first[i].raw.end());
+    void *dp = nullptr, *ds = nullptr;
+    c.check(ronk_dev_alloc(c.get(), &dp, pts.size()));
+    c.check(ronk_dev_alloc(c.get(), &ds, sc.size()));
+    c.check(ronk_memcpy_h2d(c.get(), dp, pts.data(), pts.size()));
+    c.check(ronk_memcpy_h2d(c.get(), ds, sc.data(), sc.size()));
+    CHECK((dist::commit(c, (const uint8_t*)dp, (const uint8_t*)ds, sc.size()).raw == std::array<uint8_t, 4>{32, 0, 59, 0}));
+    ronk_dev_free(c.get(), d); ronk_dev_free(c.get(), dp); ronk_dev_free(c.get(), ds);
+    dist::finalize(c);
+    CHECK(ronk_ntt_u64_dist(c.get(), P, 7, nullptr, 10, 1, 0) == RONK_ENCCL);   // no communicator any more
+  }
   std::printf(failures ? "%d FAILURES\n" : "cpp mirror ok\n", failures);
   return failures ? 1 : 0;
 }

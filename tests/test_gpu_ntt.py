@@ -257,3 +257,49 @@ def test_pipelined_host_submit_wait():
     for t, e in zip(bufs, exps):
         assert np.array_equal(t.numpy().view(np.uint64), e)
     c.call("ronk_ntt_u64_host_wait", 0)  # idempotent on an idle slot
+
+
+def test_opt_in_kernel_variants_agree_with_the_default():
+    """The switches read at ronk_ctx_create select alternative formulations of the same transform: the specialised
+    4096-point-per-tile kernel (RONK_FAST12=1: pairs, additive shared-memory layout, round 0 fed from HBM, n-word
+    inter-pass twiddle table) and the table form of the inter-pass twiddle under the generic kernel
+    (RONK_TW_TABLE=1).  Each must reproduce the default context's 2^24 and 2^23 transforms bit for bit, forward,
+    fused-multiply and inverse."""
+    import os
+    import torch
+    from ronkathon_b200 import Context, ops
+    c0 = ctx()
+    a = ops.splitmix_fill(c0, 1 << 24, 11, GL, "cuda")
+    m = ops.splitmix_fill(c0, 1 << 24, 12, GL, "cuda")
+    ref = {}
+    for lg in (24, 23):
+        x = a[: 1 << lg].clone()
+        ops.ntt_(c0, x, lg)
+        y = a[: 1 << lg].clone()
+        ops.ntt_mul_(c0, y, m[: 1 << lg].clone(), lg)
+        z = x.clone()
+        ops.ntt_(c0, z, lg, inverse=True)
+        c0.sync()
+        assert torch.equal(z, a[: 1 << lg])
+        ref[lg] = (x, y)
+    for env in ({"RONK_FAST12": "1"}, {"RONK_TW_TABLE": "1"}):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            c1 = Context(0, torch.cuda.current_stream().cuda_stream)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        for lg in (24, 23):
+            x = a[: 1 << lg].clone()
+            ops.ntt_(c1, x, lg)
+            y = a[: 1 << lg].clone()
+            ops.ntt_mul_(c1, y, m[: 1 << lg].clone(), lg)
+            z = x.clone()
+            ops.ntt_(c1, z, lg, inverse=True)
+            c1.sync()
+            assert torch.equal(x, ref[lg][0]) and torch.equal(y, ref[lg][1]) and torch.equal(z, a[: 1 << lg]), (env, lg)
+        c1.close()
