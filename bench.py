@@ -471,7 +471,17 @@ def run_multi(ctx, ops, dev, timed, rank, world, peak):
     import oracle
     from ronkathon_b200 import dist as rd
 
-    dctx = rd.DistContext(ctx)
+    # NCCL prints its version banner on STDOUT when a communicator is created with NCCL_DEBUG=VERSION/INFO in the
+    # environment; this program's stdout is one JSON line, so the banner goes to stderr
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dctx = rd.DistContext(ctx)
+        ctx.sync()
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
     out = {"abi": "ronk_dist_init / ronk_ntt_u64_batch_sharded / ronk_ntt_u64_dist / ronk_msm_pluto_ext_dist", "n_gpus": world}
 
     def gather_host(t):

@@ -218,22 +218,6 @@ def _bounded_checks(emu, p, g, log_n, src, padded, dst_len):
         assert np.array_equal(got, oracle.vec_mul(p, oracle.ntt_fast(p, padded), mul))
 
 
-def test_additive_layout_design_audit():
-    """tools/smem_layout_audit.py: the padding-based shared-memory layout proposed for the next round is
-    injective, bank-conflict-free in every phase and linear within a round for the 2^24 shapes; and the check
-    itself is not vacuous — without pads the same shapes do conflict."""
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("smem_layout_audit", os.path.join(HERE, "..", "tools", "smem_layout_audit.py"))
-    audit = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(audit)
-    for mode, c, c2 in (("pass1", 2, 1), ("pass2", 1, 0), ("single", 0, 0)):
-        pads = [(c + 4, 1 << c), (c + 8, 1)]
-        ok, words = audit.check_shape(f"{mode} c={c}", mode, 12, c, c2, 512, pads, verbose=False)
-        assert ok and words <= int(1.07 * (1 << (12 + c)))
-        bad, _ = audit.check_shape(f"{mode} c={c} unpadded", mode, 12, c, c2, 512, [], verbose=False)
-        assert not bad
-
-
 # ---- the specialised 4096-point-per-tile kernel (ntt12_kernel.cuh) ------------------------------------------
 @pytest.mark.parametrize("mode,lc", [(1, 2), (2, 1), (2, 2)])
 def test_additive_layout_is_injective_and_conflict_free(emu, mode, lc):

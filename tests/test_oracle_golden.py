@@ -272,3 +272,39 @@ def test_kat_provenance_is_mechanical():
     out = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout[-2000:]
     assert json.loads(out.stdout)["located"] >= 114
+
+
+def test_extended_curve_has_102_squared_points_and_exponent_102():
+    """What the histogram form of kzg::commit (msm.cu) relies on: E(F_101²): y² = x³ + 3 has 102² points (with
+    Infinity) and every point is killed by 102, so Σ s_i·P_i = Σ_P (c_P mod 102)·P.  Enumerated with the oracle's
+    own on-curve predicate and addition law (curve/mod.rs:130-139, :178-213)."""
+    q = 101
+
+    def gmul(a, b):
+        return ((a[0] * b[0] - 2 * a[1] * b[1]) % q, (a[0] * b[1] + a[1] * b[0]) % q)
+
+    roots = {}
+    for y0 in range(q):
+        for y1 in range(q):
+            roots.setdefault(gmul((y0, y1), (y0, y1)), []).append((y0, y1))
+    pts = []
+    for x0 in range(q):
+        for x1 in range(q):
+            x = (x0, x1)
+            r = gmul(gmul(x, x), x)
+            for y in roots.get(((r[0] + 3) % q, r[1]), []):
+                pts.append(bytes([x0, x1, y[0], y[1]]))
+    assert len(pts) + 1 == 102 * 102
+    rng = np.random.default_rng(1)
+    sample = [pts[i] for i in rng.choice(len(pts), 400, replace=False)] + pts[:50] + pts[-50:]
+
+    def smul(p, k):
+        acc = oracle.INF
+        for bit in bin(k)[2:]:
+            acc = oracle.point_add(acc, acc)
+            if bit == "1":
+                acc = oracle.point_add(acc, p)
+        return acc
+
+    for p in sample:
+        assert oracle.on_curve(p) and smul(p, 102) == oracle.INF
