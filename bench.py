@@ -270,7 +270,7 @@ def main():
         per.setdefault(name, []).append(ms)
     kern = {k: sum(v) / len(v) for k, v in per.items()}
     dom = max(kern, key=kern.get)
-    stages = {"ntt_pass1": 12, "ntt_pass2": 12}
+    stages = {"ntt_pass1": 12, "ntt_pass2": 12, "ntt3_pass1": 8, "ntt3_pass2": 8, "ntt3_pass3": 8}
     peak, peak_src = measured_peaks()
     # algorithmic bytes of one launch = 16·n · (butterfly stages this launch does / 24)
     alg_bytes = ALG_BYTES_PER_NTT * stages.get(dom, 24) / 24

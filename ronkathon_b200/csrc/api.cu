@@ -41,6 +41,11 @@ int ronk_ctx_create(ronk_ctx** out, int device, void* stream) {
   };
   ctx->tune.pf_dist = env_int("RONK_PF_DIST", 1);
   ctx->tune.pf_dist2 = env_int("RONK_PF_DIST2", 1);
+  ctx->tune.pdl = env_int("RONK_PDL", 1);
+  ctx->tune.ntt3 = env_int("RONK_NTT3", 1);
+  ctx->tune.ntt3_pdl = env_int("RONK_NTT3_PDL", 1);
+  ctx->tune.ntt3_t1 = env_int("RONK_NTT3_T1", 0);
+  ctx->tune.ntt3_min_batch16 = env_int("RONK_NTT3_MIN_BATCH16", 1);
   ctx->tune.single_tile_log = env_int("RONK_SINGLE_TILE_LOG", 12);
   ctx->tune.tile1 = env_int("RONK_TILE1", 14);
   ctx->tune.tile2 = env_int("RONK_TILE2", 13);
@@ -81,8 +86,12 @@ int ronk_ctx_destroy(ronk_ctx* ctx) {
     }
     if (p.tw_lo) cudaFree(p.tw_lo);
     if (p.tw_hi_inv) cudaFree(p.tw_hi_inv);
-    for (int d = 0; d < 2; d++)
+    for (int d = 0; d < 2; d++) {
       for (auto& t : p.tw_full[d]) cudaFree(t.second);
+      if (p.tw256[d]) cudaFree(p.tw256[d]);
+      if (p.t2[d]) cudaFree(p.t2[d]);
+      if (p.t1[d]) cudaFree(p.t1[d]);
+    }
   }
   for (auto& r : ctx->prof_log) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
   for (int i = 0; i < ronk_ctx::kSlots; i++) {

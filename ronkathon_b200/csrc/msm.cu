@@ -118,7 +118,8 @@ constexpr u32 MSM_XS = Q101 * Q101;   // 10201 x values
 constexpr u32 MSM_BINS = 2 * MSM_XS;  // 20402
 constexpr u32 MSM_EXP = 102;          // group exponent of E(F_101²) ≅ (Z/102)²
 constexpr int MSM_HIST_THREADS = 1024;
-constexpr int MSM_FIN_THREADS = 256;
+constexpr int MSM_FIN_THREADS = 256;   // bins per finishing CTA
+constexpr u32 MSM_FIN_GROUPS = 4;      // thread groups sharing the column sum of those bins (blockDim = 1024)
 
 RONK_DEV u32 y_bit(u32 y0, u32 y1) { return y0 ? (y0 > 50u) : (y1 > 50u); }
 
@@ -155,6 +156,7 @@ msm_hist_kernel(const u32* __restrict__ points, const uint8_t* __restrict__ scal
   u32* hist = msm_smem;                                      // [MSM_BINS]
   uint16_t* ytab = reinterpret_cast<uint16_t*>(hist + MSM_BINS);  // [MSM_BINS]
   const u32 t = threadIdx.x;
+  asm volatile("griddepcontrol.launch_dependents;");  // the finishing kernel may set up while this one runs (PDL)
   for (u32 i = t; i < MSM_BINS; i += MSM_HIST_THREADS) hist[i] = 0u;
   {  // 40 804 bytes of table, 4 at a time
     const u32* src = reinterpret_cast<const u32*>(ytab_g);
@@ -222,31 +224,44 @@ RONK_DEV void msm_cta_tree(u32* red, u32 t, u32 len, const uint8_t* inv) {
 #endif
 }
 
-__global__ void __launch_bounds__(MSM_FIN_THREADS)
+__global__ void __launch_bounds__(MSM_FIN_THREADS * MSM_FIN_GROUPS)
 msm_hist_finish_kernel(const u32* __restrict__ partial, u32 sets, u32* __restrict__ ghist,
                        const uint16_t* __restrict__ ytab, u32* __restrict__ cta_sum, u32* __restrict__ done_counter,
                        volatile u32* host_result) {
   __shared__ u32 red[MSM_FIN_THREADS];
+  __shared__ u32 colsum[MSM_FIN_GROUPS][MSM_FIN_THREADS];
   __shared__ uint8_t inv[104];
   __shared__ u32 is_last;
-  const u32 t = threadIdx.x;
-  build_inv_table(inv, t, MSM_FIN_THREADS);
+  const u32 t = threadIdx.x & (MSM_FIN_THREADS - 1u), grp = threadIdx.x / MSM_FIN_THREADS;
+  build_inv_table(inv, threadIdx.x, MSM_FIN_THREADS * MSM_FIN_GROUPS);
   const u32 bin = blockIdx.x * MSM_FIN_THREADS + t;
-  u32 c = 0;
-  if (bin < MSM_BINS) {
-    // 16 loads of the column in flight per step: the column sum is a chain of L2 latencies otherwise
-    // (148 partial histograms: 10 steps instead of 148)
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the histogram kernel has completed and its stores are visible
+  // Column sum over the partial histograms: the kernel's long pole (ncu: long_scoreboard 35 of 48 stall cycles per
+  // instruction).  MSM_FIN_GROUPS thread groups take every MSM_FIN_GROUPS-th histogram with 16 loads in flight each,
+  // so 148 histograms are 3 dependent steps instead of 10.
+  {
     u32 acc16[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) acc16[k] = 0u;
-    u32 g = 0;
-    for (; g + 16 <= sets; g += 16) {
+    if (bin < MSM_BINS) {
+      u32 g = grp;
+      for (; g + 15u * MSM_FIN_GROUPS < sets; g += 16u * MSM_FIN_GROUPS) {
 #pragma unroll
-      for (int k = 0; k < 16; k++) acc16[k] += partial[(size_t)(g + k) * MSM_BINS + bin];
+        for (int k = 0; k < 16; k++) acc16[k] += partial[(size_t)(g + (u32)k * MSM_FIN_GROUPS) * MSM_BINS + bin];
+      }
+      for (; g < sets; g += MSM_FIN_GROUPS) acc16[0] += partial[(size_t)g * MSM_BINS + bin];
     }
-    for (; g < sets; g++) acc16[0] += partial[(size_t)g * MSM_BINS + bin];
+    u32 part = 0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) c += acc16[k];
+    for (int k = 0; k < 16; k++) part += acc16[k];
+    colsum[grp][t] = part;
+  }
+  __syncthreads();
+  if (grp) return;  // the remaining work is one thread per bin
+  u32 c = 0;
+  if (bin < MSM_BINS) {
+#pragma unroll
+    for (u32 k = 0; k < MSM_FIN_GROUPS; k++) c += colsum[k][t];
     if (ghist) {
       c += ghist[bin];
       ghist[bin] = 0u;  // self-cleaning: ready for the next call
@@ -373,8 +388,23 @@ static int msm_hist_device(ronk_ctx* ctx, const uint8_t* points, size_t n_points
   RONK_TRY(check_launch(ctx, "msm_hist_kernel"));
   {
     LaunchScope ls(ctx, "msm_hist_finish");
-    msm_hist_finish_kernel<<<fin_ctas, MSM_FIN_THREADS, 0, ctx->stream>>>(
-        partial, (u32)ctas, ghist, (const uint16_t*)ctx->msm_ytab, cta_sum, (u32*)ctx->msm_done, (volatile u32*)(host_dev + 1));
+    if (ctx->tune.pdl && !ctx->prof) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(fin_ctas);
+      cfg.blockDim = dim3(MSM_FIN_THREADS * MSM_FIN_GROUPS);
+      cfg.stream = ctx->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      RONK_CUDA(ctx, cudaLaunchKernelEx(&cfg, msm_hist_finish_kernel, (const u32*)partial, (u32)ctas, ghist,
+                                        (const uint16_t*)ctx->msm_ytab, cta_sum, (u32*)ctx->msm_done,
+                                        (volatile u32*)(host_dev + 1)));
+    } else {
+      msm_hist_finish_kernel<<<fin_ctas, MSM_FIN_THREADS * MSM_FIN_GROUPS, 0, ctx->stream>>>(
+          partial, (u32)ctas, ghist, (const uint16_t*)ctx->msm_ytab, cta_sum, (u32*)ctx->msm_done, (volatile u32*)(host_dev + 1));
+    }
   }
   RONK_TRY(check_launch(ctx, "msm_hist_finish_kernel"));
   RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

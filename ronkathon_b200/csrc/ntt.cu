@@ -6,6 +6,7 @@
 #include <type_traits>
 
 #include "ntt12_kernel.cuh"
+#include "ntt3_kernel.cuh"
 #include "ntt_kernel.cuh"
 #include "ronk_internal.h"
 
@@ -127,7 +128,24 @@ static int launch_tile_nb(ronk_ctx* ctx, const F& f, const NttTileArgs& A0, u32 
   RONK_TRY(ensure_smem_attr(ctx, ntt_tile_kernel<F, MODE, INV, NTHR, MINB, BOUNDED, FMUL>, 226 * 1024));
   {
     LaunchScope ls(ctx, name);
-    ntt_tile_kernel<F, MODE, INV, NTHR, MINB, BOUNDED, FMUL><<<tiles, NTHR, smem, ctx->stream>>>(f, A);
+    // measured (r02g): the early launch gains 2 µs on launch-bound jobs (2^14…2^18: 16.7 → 14.6 µs) and LOSES 3 % on a
+    // 2^24 transform (0.381 → 0.392 ms: the waiting CTAs start in lockstep), so only small jobs take it
+    if (MODE == MODE_PASS2 && ctx->tune.pdl && !ctx->prof && (((u64)tiles << A.tile_log) <= ((u64)1 << 21))) {
+      // pass 2 directly follows its pass 1 on the stream: let it start early (the kernel waits at griddepcontrol.wait)
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(tiles);
+      cfg.blockDim = dim3(NTHR);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = ctx->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      RONK_CUDA(ctx, cudaLaunchKernelEx(&cfg, ntt_tile_kernel<F, MODE, INV, NTHR, MINB, BOUNDED, FMUL>, f, A));
+    } else {
+      ntt_tile_kernel<F, MODE, INV, NTHR, MINB, BOUNDED, FMUL><<<tiles, NTHR, smem, ctx->stream>>>(f, A);
+    }
   }
   return check_launch(ctx, name);
 }
@@ -190,6 +208,87 @@ static int launch_tile(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tile
   return launch_tile_n<F, MODE, INV, 32, 2>(ctx, f, A, tiles, name);
 }
 
+// ---- transforms as passes of 256-point tiles (ntt3_kernel.cuh): n = 2^24 (three passes) and n = 2^16 (two) -------
+template <class F, int PASS, bool INV, int LOGN, bool BOUNDED>
+static int launch3(ronk_ctx* ctx, const F& f, const Ntt3Args& A, const char* name, bool dependent) {
+  const unsigned tiles = A.batch * (LOGN == 24 ? 4096u : 16u);
+  LaunchScope ls(ctx, name);
+  if (dependent && ctx->tune.ntt3_pdl && !ctx->prof) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tiles);
+    cfg.blockDim = dim3(N3_THREADS);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RONK_CUDA(ctx, cudaLaunchKernelEx(&cfg, ntt3_kernel<F, PASS, INV, LOGN, BOUNDED>, f, A));
+  } else {
+    ntt3_kernel<F, PASS, INV, LOGN, BOUNDED><<<tiles, N3_THREADS, 0, ctx->stream>>>(f, A);
+  }
+  return RONK_OK;
+}
+
+// data = NTT(src [zero-extended from src_len]) [⊙ mul], the first dst_len outputs stored.  Pass 1 src → workspace, pass 2
+// in place in the workspace (its input and output views coincide), pass 3 workspace → data: src is only read, data only
+// written by the last pass, so src == data (in place) and a short data buffer (dst_len words) are both fine.
+template <class F, bool INV, int LOGN, bool BOUNDED>
+static int run_ntt3(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, const u64* src, const u64* mul, u32 batch,
+                    u64 src_len, u64 dst_len) {
+  NttPlan& pl = const_cast<NttPlan&>(pl_c);
+  const int d = INV ? 1 : 0;
+  const u64 p = pl.p, n = (u64)1 << LOGN;
+  if (!pl.tw256[d]) {  // one-time tables for this direction
+    u64 w = h_powmod(pl.g, (p - 1) / n, p);
+    if (INV) w = h_powmod(w, p - 2, p);
+    RONK_TRY(build_table(ctx, f, h_powmod(w, n >> 8, p), 1, &pl.tw256[d], 256));
+    RONK_CUDA(ctx, cudaMalloc((void**)&pl.t2[d], 65536 * sizeof(u64)));
+    const u64 ninv = INV ? h_powmod(n % p, p - 2, p) : 1;
+    {
+      LaunchScope ls(ctx, "ntt3_t2");
+      ntt3_t2_kernel<F><<<256, 256, 0, ctx->stream>>>(f, h_powmod(w, n >> 16, p), ninv, pl.t2[d]);
+    }
+    RONK_TRY(check_launch(ctx, "ntt3_t2_kernel"));
+  }
+  if (LOGN == 24 && ctx->tune.ntt3_t1 && !pl.t1[d]) {  // optional 128 MiB table of the pass-1 twiddles (no memory: stay stepped)
+    if (cudaMalloc((void**)&pl.t1[d], n * sizeof(u64)) == cudaSuccess) {
+      LaunchScope ls(ctx, "ntt3_t1");
+      ntt3_t1_kernel<F><<<(unsigned)(n / 256), 256, 0, ctx->stream>>>(f, pl.tw_lo, pl.tw2, INV ? 1 : 0, pl.t1[d]);
+    } else {
+      cudaGetLastError();
+      pl.t1[d] = nullptr;
+    }
+    RONK_TRY(check_launch(ctx, "ntt3_t1_kernel"));
+  }
+  if (batch > (0x7FFFFFFFu >> 12)) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
+  RONK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, ((size_t)batch << LOGN) * sizeof(u64)));
+  Ntt3Args A = {};
+  A.t1 = ctx->tune.ntt3_t1 ? pl.t1[d] : nullptr;
+  A.tw256 = pl.tw256[d];
+  A.tw_lo = pl.tw_lo;
+  A.tw_hi = pl.tw2;   // ω_n^(4096 y), plain: the n^-1 of the inverse rides on the pass-2 table
+  A.t2 = pl.t2[d];
+  A.batch = batch;
+  A.src_len = src_len;
+  A.dst_len = dst_len;
+  A.src = src;
+  A.dst = (u64*)ctx->ws;
+  if (LOGN == 24) {
+    RONK_TRY((launch3<F, 1, INV, LOGN, BOUNDED>(ctx, f, A, INV ? "intt3_pass1" : "ntt3_pass1", false)));
+    RONK_TRY(check_launch(ctx, "ntt3 pass 1"));
+    A.src = (const u64*)ctx->ws;
+  }
+  RONK_TRY((launch3<F, 2, INV, LOGN, BOUNDED && LOGN == 16>(ctx, f, A, INV ? "intt3_pass2" : "ntt3_pass2", LOGN == 24)));
+  RONK_TRY(check_launch(ctx, "ntt3 pass 2"));
+  A.src = (const u64*)ctx->ws;
+  A.dst = data;
+  A.mul_src = mul;
+  A.flags = mul ? NTT_FLAG_MUL : 0;
+  RONK_TRY((launch3<F, 3, INV, LOGN, BOUNDED>(ctx, f, A, INV ? "intt3_pass3" : "ntt3_pass3", true)));
+  return check_launch(ctx, "ntt3 pass 3");
+}
+
 // src == nullptr: in place.  Otherwise (batch == 1) the transform reads src[0, src_len) zero-extended to n
 // words and writes data[0, dst_len): the zero padding of poly_mul's operands and the clipping of its
 // result happen inside the load / store phases instead of in separate copy kernels.
@@ -212,6 +311,16 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
     A.mul_mask = mul_mask;
     if (tiles > 0x7FFFFFFFULL) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
     return launch_tile<F, MODE_SINGLE, INV>(ctx, f, A, (u32)tiles, INV ? "intt_single" : "ntt_single");
+  }
+  if constexpr (std::is_same<F, GoldilocksField>::value) {
+    if (ctx->tune.ntt3 && mul_mask == ~0ULL && !(INV && mul)) {
+      const bool bounded = src_len != NTT_UNBOUNDED || dst_len != NTT_UNBOUNDED;  // only ever with batch == 1
+      // 2^16: worth it once the grid fills the GPU (16 tiles per transform); single transforms stay launch-bound
+      if (log_n == 24 && !bounded) return run_ntt3<F, INV, 24, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
+      if (log_n == 24 && batch == 1) return run_ntt3<F, INV, 24, true>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
+      if (log_n == 16 && !bounded && batch >= (u32)ctx->tune.ntt3_min_batch16)
+        return run_ntt3<F, INV, 16, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
+    }
   }
   const size_t bytes = ((size_t)batch << log_n) * sizeof(u64);
   RONK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, bytes));

@@ -1,0 +1,248 @@
+// ntt3_kernel.cuh — the 2^24-point transform as THREE passes of 256-point transforms (round 2).
+//
+// Same map as Polynomial::fft / ifft (src/polynomial/mod.rs:273-323, :430-484): X[k] = Σ_j a_j ω^(jk), natural order in
+// and out, canonical residues.  With j = j1·2^16 + j2·2^8 + j3 and k = k1 + k2·2^8 + k3·2^16 (all digits < 256):
+//
+//   pass 1  A1[k1, j2, j3] = ( Σ_j1 ω_256^(j1 k1) a[j1, j2, j3] ) · ω_n^(k1·(256 j2 + j3))        in place on the data
+//   pass 2  A2[k1, k2, j3] = ( Σ_j2 ω_256^(j2 k2) A1[k1, j2, j3] ) · ω_65536^(k2 j3)               data → workspace
+//   pass 3  X[k1 + 256 k2 + 65536 k3] = Σ_j3 ω_256^(j3 k3) A2[k1, k2, j3]                          workspace → data
+//
+// Why three passes when two suffice (ntt_kernel.cuh): the two-pass kernel needs 64–128 KiB tiles, so an SM holds 16 warps
+// (4 per scheduler) and every tile goes through three CTA barriers and four shared-memory round trips; measured, it runs at
+// 68 % of its own integer-pipe floor and stripping a fifth of its instructions did not make it faster:
+// it is bound by latency hiding, not by instruction count.  A 256-point transform per tile needs 4096 elements (16 columns:
+// every global access is a full 128-byte line in all three passes) = 35 KB of shared memory and 128 threads: six CTAs per
+// SM (24 warps), ONE barrier and ONE shared-memory round trip per tile:
+//
+//   round 0   each thread loads its two radix-16 groups (digit d1 of the transform index) straight from HBM into
+//             registers, runs the shift-twiddle network, multiplies by ω_256^(d0·k_hi) and writes the tile;
+//   barrier
+//   round 1   radix-16 over digit d0 from shared memory, then the inter-pass twiddle and the stores — straight from the
+//             registers to the rows bitrev8 assigns them (no un-bit-reversing pass through shared memory).
+//
+// HBM traffic is 3 reads + 3 writes of the data (805 MB at 2^24) instead of 2 + 2: the kernel is integer-pipe-bound with
+// HBM at < 20 % of its peak, so the bytes are there to spend.  General multiplications per element: 3·15/16 (inner) + 2
+// (pass 1: stepped ω_n^(k1·m), apply) + 1 (pass 2: 64 Ki-entry table, L2-resident) = 5.8, as in the two-pass kernel.
+//
+// Tile index e = (d1 << 8) | (d0 << 4) | c  (transform index i = 16·d1 + d0, column c); shared-memory word
+// word(e) = 272·d1 + 17·d0 + c: additive (every access is [R + imm]) and conflict-free for lanes that differ in c
+// (passes 1, 2 and every round-1 read) as well as for lanes that differ in d0 (round-0 writes of pass 3, whose
+// transform axis is the contiguous one): bank = (c + d0) mod 16.
+#pragma once
+#include "ntt_kernel.cuh"
+
+namespace ronk {
+
+// 1: the two groups of a thread run as a loop — half the code (the kernel's top stall was no_instruction: six CTAs
+// at different places of a 100 KB instruction stream); 2: both groups unrolled
+#ifndef RONK_NTT3_UNROLL_GROUPS
+#define RONK_NTT3_UNROLL_GROUPS 1
+#endif
+constexpr u32 N3_THREADS = 128;
+constexpr u32 N3_TILE_WORDS = 16 * 272;  // 4352 words = 34 816 B
+RONK_HD constexpr u32 n3_word(u32 d1, u32 d0, u32 c) { return 272u * d1 + 17u * d0 + c; }
+RONK_HD constexpr u32 n3_br4(int j) { return (u32)(((j & 1) << 3) | ((j & 2) << 1) | ((j & 4) >> 1) | ((j & 8) >> 3)); }
+
+struct Ntt3Args {
+  const u64* src;
+  u64* dst;
+  const u64* tw256;    // ω_256^x (direction applied), x < 256, twiddle form
+  const u64* tw_lo;    // pass 1: ω_n^x, x < 4096 (twiddle form)
+  const u64* tw_hi;    // pass 1: ω_n^(4096 y), y < 4096
+  const u64* t2;       // pass 2: ω_65536^(±k2·j3) [· n^-1 for the inverse], [k2][j3], twiddle form
+  const u64* t1;       // pass 1, optional: ω_n^(±k1·m) as an n-word table [k1][m] (else stepped from tw_lo / tw_hi)
+  const u64* mul_src;  // pass 3, optional: point-wise multiplier indexed like the output
+  u64 src_len;         // BOUNDED kernels (batch = 1): the first pass reads src[0, src_len) zero-extended,
+  u64 dst_len;         //                               the last pass stores dst[0, dst_len) only
+  u32 batch;
+  u32 flags;           // NTT_FLAG_MUL
+};
+
+// ---- round 0: 16 elements per group straight from global memory ----
+// PASS 1, 2: group g ↔ (d0 = g >> 4, c = g & 15): element q is row i = 16 q + d0 of the tile, column c.
+// PASS 3:    group g ↔ (col = g >> 4, d0 = g & 15): element q is i = 16 q + d0 of column col (i is the contiguous axis).
+template <class F, int PASS, bool INV, bool BOUNDED = false>
+RONK_DEV void n3_round0(const F& f, u64* smem, const Ntt3Args& A, u64 tile_base, u64 row_stride, u64 col_stride, u32 tid) {
+#if RONK_NTT3_UNROLL_GROUPS == 1
+#pragma unroll 1
+#else
+#pragma unroll
+#endif
+  for (int h = 0; h < 2; h++) {
+    const u32 g = tid + (u32)h * N3_THREADS;
+    const u32 d0 = (PASS == 3) ? (g & 15u) : (g >> 4), c = (PASS == 3) ? (g >> 4) : (g & 15u);
+    const u64* p = A.src + tile_base + (u64)d0 * row_stride + (u64)c * col_stride;
+    u64 x[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      if (BOUNDED) {
+        const u64 idx = tile_base + (u64)d0 * row_stride + (u64)c * col_stride + (u64)q * 16u * row_stride;
+        x[q] = idx < A.src_len ? p[(u64)q * 16u * row_stride] : 0;
+      } else {
+        x[q] = p[(u64)q * 16u * row_stride];
+      }
+    }
+    radix_network<4, INV>(f, x);
+    const u64* tw = A.tw256 + d0;  // ω_256^(d0·k_hi), k_hi = bitrev4(register index)
+    u64* s = smem + n3_word(0, d0, c);
+    s[0] = x[0];
+#pragma unroll
+    for (int j = 1; j < 16; j++) s[n3_word((u32)j, 0, 0)] = f.mul_tw(x[j], ld_tw(tw + (n3_br4(j) - 1u) * d0));
+  }
+}
+
+// ---- round 1 + inter-pass twiddle + stores ----
+// group g ↔ (d1 = g >> 4, c = g & 15).  Register q is tile position d0 = q, i.e. output k = bitrev8(16 d1 + q) =
+// 16·bitrev4(q) + bitrev4(d1); it goes to row k of the output view, column c.
+template <class F, int PASS, bool INV, bool BOUNDED = false>
+RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile_base, u64 row_stride, u32 m_base, u32 tid) {
+#if RONK_NTT3_UNROLL_GROUPS == 1
+#pragma unroll 1
+#else
+#pragma unroll
+#endif
+  for (int h = 0; h < 2; h++) {
+    const u32 g = tid + (u32)h * N3_THREADS;
+    const u32 d1 = g >> 4, c = g & 15u;
+    const u64* s = smem + n3_word(d1, 0, c);
+    u64 x[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) x[q] = s[n3_word(0, (u32)q, 0)];
+    radix_network<4, INV>(f, x);
+    const u32 b = bitrev(d1, 4);
+    u64* o = A.dst + tile_base + (u64)b * row_stride + c;   // row k = 16 q' + b, q' = bitrev4(register index)
+    if (PASS == 1 && A.t1) {
+      // ω_n^(±k1·m) from the n-word table [k1][m]: the same offsets as the stores, one coalesced load each
+      const u64* t = A.t1 + ((u64)b << 16) + m_base + c;
+      u64 w[16];
+#pragma unroll
+      for (int qp = 0; qp < 16; qp++) w[qp] = ld_tw(t + ((u64)qp << 20));
+#pragma unroll
+      for (int qp = 0; qp < 16; qp++) o[(u64)qp * 16u * row_stride] = f.mul_tw(x[n3_br4(qp)], w[qp]);
+    } else if (PASS == 1) {
+      // ω_n^(±k1·m), m = 256 j2 + j3 (this thread's column), k1 = 16 q' + b: stepped over q' with ρ = ω_n^(±16 m)
+      const u32 m = m_base + c;
+      u32 ex0 = m * b, exd = m << 4;
+      if (INV) { ex0 = (0u - ex0) & 0xFFFFFFu; exd = (0u - exd) & 0xFFFFFFu; }
+      u64 w = f.mul_tw(ld_tw(A.tw_lo + (ex0 & 4095u)), ld_tw(A.tw_hi + (ex0 >> 12)));
+      const u64 rho = f.mul_tw(ld_tw(A.tw_lo + (exd & 4095u)), ld_tw(A.tw_hi + (exd >> 12)));
+#pragma unroll
+      for (int qp = 0; qp < 16; qp++) {
+        o[(u64)qp * 16u * row_stride] = f.mul_tw(x[n3_br4(qp)], w);
+        if (qp < 15) w = f.mul_tw(w, rho);
+      }
+    } else if (PASS == 2) {
+      // ω_65536^(±k2·j3) from the 64 Ki-entry table [k2][j3]; m_base = first j3 of the tile
+      const u64* t = A.t2 + ((u64)b << 8) + m_base + c;
+      u64 w[16];
+#pragma unroll
+      for (int qp = 0; qp < 16; qp++) w[qp] = ld_tw(t + ((u64)qp << 12));
+#pragma unroll
+      for (int qp = 0; qp < 16; qp++) o[(u64)qp * 16u * row_stride] = f.mul_tw(x[n3_br4(qp)], w[qp]);
+    } else {
+      const u64 idx0 = tile_base + (u64)b * row_stride + c;   // index of row q' = 0 within the transform (BOUNDED: batch = 1)
+      if (A.flags & NTT_FLAG_MUL) {
+        const u64* mp = A.mul_src + tile_base + (u64)b * row_stride + c;
+        u64 w[16];
+#pragma unroll
+        for (int qp = 0; qp < 16; qp++) w[qp] = mp[(u64)qp * 16u * row_stride];
+#pragma unroll
+        for (int qp = 0; qp < 16; qp++)
+          if (!BOUNDED || idx0 + (u64)qp * 16u * row_stride < A.dst_len) o[(u64)qp * 16u * row_stride] = f.mul(x[n3_br4(qp)], w[qp]);
+      } else {
+#pragma unroll
+        for (int qp = 0; qp < 16; qp++)
+          if (!BOUNDED || idx0 + (u64)qp * 16u * row_stride < A.dst_len) o[(u64)qp * 16u * row_stride] = x[n3_br4(qp)];
+      }
+    }
+  }
+}
+
+// tile → addresses.  LOGN = 24: 4096 tiles per transform in every pass:
+//   pass 1: tile = (j2, s): rows j1 (stride 65536), columns j3 = 16 s + c           — in and out views identical
+//   pass 2: tile = (k1, s): rows j2 (stride 256),   columns j3 = 16 s + c           — in and out views identical
+//   pass 3: tile = (k2, t): input column col ↔ k1 = 16 t + col (stride 65536), index i = j3 contiguous;
+//                           output rows k3 (stride 65536), columns k1 = 16 t + col
+// LOGN = 16 (n = 256·256, BASELINE config 5): the same two kernels without pass 1 — 16 tiles per transform:
+//   pass 2: tile = s: rows j1 (stride 256), columns j2 = 16 s + c, twiddle ω_n^(k1·j2) = the [k1][j2] table
+//   pass 3: tile = t: input column col ↔ k1 = 16 t + col (stride 256), i = j2 contiguous; output X[k1 + 256 k2]
+template <int PASS, int LOGN>
+RONK_DEV void n3_tile_geometry(u32 tile, u64* in_base, u64* in_row, u64* in_col, u64* out_base, u64* out_row, u32* m_base) {
+  if (LOGN == 16) {
+    const u64 b = tile >> 4;
+    const u32 lo = tile & 15u;
+    if (PASS == 2) {
+      *in_base = *out_base = (b << 16) + 16u * lo;
+      *in_row = *out_row = 256;
+      *in_col = 1;
+      *m_base = 16u * lo;
+    } else {
+      *in_base = (b << 16) + ((u64)(16u * lo) << 8);
+      *in_row = 1;
+      *in_col = 256;
+      *out_base = (b << 16) + 16u * lo;
+      *out_row = 256;
+      *m_base = 0;
+    }
+    return;
+  }
+  const u64 b = tile >> 12;
+  const u32 hi = (tile >> 4) & 255u, lo = tile & 15u;
+  if (PASS == 1) {        // hi = j2, lo = s
+    *in_base = *out_base = (b << 24) + ((u64)hi << 8) + 16u * lo;
+    *in_row = *out_row = 65536;
+    *in_col = 1;
+    *m_base = (hi << 8) + 16u * lo;
+  } else if (PASS == 2) { // hi = k1, lo = s
+    *in_base = *out_base = (b << 24) + ((u64)hi << 16) + 16u * lo;
+    *in_row = *out_row = 256;
+    *in_col = 1;
+    *m_base = 16u * lo;
+  } else {                // hi = k2, lo = t
+    *in_base = (b << 24) + ((u64)(16u * lo) << 16) + ((u64)hi << 8);
+    *in_row = 1;
+    *in_col = 65536;
+    *out_base = (b << 24) + ((u64)hi << 8) + 16u * lo;
+    *out_row = 65536;
+    *m_base = 0;
+  }
+}
+
+#if defined(__CUDACC__)
+template <class F, int PASS, bool INV, int LOGN, bool BOUNDED>
+__global__ void __launch_bounds__(N3_THREADS, 6) ntt3_kernel(const F f, const Ntt3Args A) {
+  __shared__ u64 smem[N3_TILE_WORDS];
+  const u32 tid = threadIdx.x;
+  u64 in_base, in_row, in_col, out_base, out_row;
+  u32 m_base;
+  n3_tile_geometry<PASS, LOGN>(blockIdx.x, &in_base, &in_row, &in_col, &out_base, &out_row, &m_base);
+  // programmatic dependent launch: a pass may be scheduled while its predecessor's last wave is still running; it must
+  // not touch the predecessor's output before griddepcontrol.wait (no-ops without the launch attribute)
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  n3_round0<F, PASS, INV, BOUNDED && PASS == (LOGN == 24 ? 1 : 2)>(f, smem, A, in_base, in_row, in_col, tid);  // src_len: first pass only
+  __syncthreads();
+  n3_round1<F, PASS, INV, BOUNDED>(f, smem, A, out_base, out_row, m_base, tid);
+}
+
+// T1[k1][m] = ω_n^(±k1·m), k1 < 256, m < 65536 (twiddle form), from the two-level tables
+template <class F>
+__global__ void ntt3_t1_kernel(const F f, const u64* __restrict__ tw_lo, const u64* __restrict__ tw_hi, int inverse, u64* __restrict__ out) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;  // < 2^24
+  const u32 k1 = i >> 16, m = i & 0xFFFFu;
+  u32 ex = (k1 * m) & 0xFFFFFFu;
+  if (inverse) ex = (0u - ex) & 0xFFFFFFu;
+  out[i] = f.mul_tw(tw_lo[ex & 4095u], tw_hi[ex >> 12]);
+}
+
+// T2[k2][j3] = to_tw(ω_65536^(±k2·j3) · s): 64 Ki entries
+template <class F>
+__global__ void ntt3_t2_kernel(const F f, u64 w65536, u64 s, u64* out) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 65536u) return;
+  const u32 k2 = i >> 8, j3 = i & 255u;
+  out[i] = f.to_tw(f.mul(field_pow(f, w65536, (u64)(k2 * j3)), s));
+}
+#endif
+
+}  // namespace ronk

@@ -697,6 +697,11 @@ __global__ void __launch_bounds__(NTHR, MINB) ntt_tile_kernel(const F f, const N
     mbar_expect_tx(bar, A.tw_words * 8u);
     tma_bulk_g2s(tw, A.tw_tile, A.tw_words * 8u, bar);  // lands while the tile itself is being loaded
   }
+  // Programmatic dependent launch: pass 1 lets pass 2's CTAs be scheduled as soon as its own last wave is running;
+  // they set up (mbarrier, twiddle TMA) and then wait here until pass 1 has completed and its workspace writes are
+  // visible.  Both instructions are no-ops when the launch carries no PDL attribute.
+  if (MODE == MODE_PASS1) asm volatile("griddepcontrol.launch_dependents;");
+  if (MODE == MODE_PASS2) asm volatile("griddepcontrol.wait;" ::: "memory");
   if ((RONK_LOAD_V0_MASK >> MODE) & 1) ntt_load_phase_v0<F, MODE, BOUNDED>(smem, A, tile, tid, NTHR);
   else ntt_load_phase<F, MODE, BOUNDED>(smem, A, tile, tid, NTHR);
   if (MODE == MODE_PASS1 && A.prefetch_dist && tile + A.prefetch_dist < gridDim.x)

@@ -36,12 +36,21 @@ struct NttPlan {
   // full inter-pass twiddle tables ω_n^(±j2·k1) [· n^-1] in the pass-1 workspace layout, per direction and
   // per log2(C2) of that layout (built on first use; n words each)
   std::map<u32, u64*> tw_full[2];
+  // three-pass 2^24 transform (ntt3_kernel.cuh): ω_256^x and the 64 Ki-entry pass-2 table, per direction
+  u64* tw256[2] = {nullptr, nullptr};
+  u64* t2[2] = {nullptr, nullptr};
+  u64* t1[2] = {nullptr, nullptr};  // optional n-word pass-1 twiddle table (RONK_NTT3_T1=1)
 };
 
 }  // namespace ronk
 
 // Tuning switches, read from the environment ONCE at ronk_ctx_create (never on the launch path).
 struct ronk_tune {
+  int ntt3_min_batch16 = 1; // RONK_NTT3_MIN_BATCH16: smallest batch of 2^16-point transforms that takes the 256-point-tile kernels
+  int ntt3_t1 = 0;          // RONK_NTT3_T1: pass-1 twiddles ω_n^(k1·m) from a 128 MiB table instead of stepping
+  int ntt3_pdl = 1;         // RONK_NTT3_PDL: programmatic dependent launch between the three passes
+  int ntt3 = 1;             // RONK_NTT3: 2^24-point transforms as three passes of 256-point tiles (ntt3_kernel.cuh)
+  int pdl = 1;              // RONK_PDL: programmatic dependent launch of pass 2 behind pass 1
   int pf_dist2 = 1;         // RONK_PF_DIST2: the same for pass 2 of the specialised kernel (round 0 fed from HBM)
   int pf_dist = 1;          // RONK_PF_DIST: pass-1 L2 prefetch distance in waves of co-resident CTAs (0 = off)
   int single_tile_log = 12; // RONK_SINGLE_TILE_LOG: preferred tile size when several small transforms share a tile

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../ronkathon_b200/csrc/ntt12_kernel.cuh"
+#include "../../ronkathon_b200/csrc/ntt3_kernel.cuh"
 #include "../../ronkathon_b200/csrc/ntt_kernel.cuh"
 
 using namespace ronk;
@@ -196,6 +197,60 @@ int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 l
   return 0;
 }
 
+// The three-pass 2^24 transform (ntt3_kernel.cuh), phase by phase like ntt3_kernel; tables as run_ntt3() builds them.
+template <class F, int PASS, bool INV, int LOGN, bool BOUNDED = false>
+void run_pass3(const F& f, const Ntt3Args& A) {
+  std::vector<u64> smem(N3_TILE_WORDS);
+  for (u32 tile = 0; tile < A.batch * (LOGN == 24 ? 4096u : 16u); tile++) {
+    u64 in_base, in_row, in_col, out_base, out_row;
+    u32 m_base;
+    n3_tile_geometry<PASS, LOGN>(tile, &in_base, &in_row, &in_col, &out_base, &out_row, &m_base);
+    for (u32 t = 0; t < N3_THREADS; t++) n3_round0<F, PASS, INV, BOUNDED && PASS == (LOGN == 24 ? 1 : 2)>(f, smem.data(), A, in_base, in_row, in_col, t);
+    for (u32 t = 0; t < N3_THREADS; t++) n3_round1<F, PASS, INV, BOUNDED>(f, smem.data(), A, out_base, out_row, m_base, t);
+  }
+}
+int g_ntt3_t1 = 0;  // 1: pass-1 twiddles from the n-word table
+template <class F, bool INV, int LOGN, bool BOUNDED = false>
+int run3(const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 batch, const u64* src = nullptr, u64 src_len = ~0ULL,
+         u64 dst_len = ~0ULL) {
+  const u64 n = (u64)1 << LOGN;
+  u64 w = h_powmod(g, (p - 1) / n, p);
+  const u64 wf = w;
+  if (INV) w = h_powmod(w, p - 2, p);
+  auto tw256 = table(f, h_powmod(w, n >> 8, p), 1, 256);
+  std::vector<u64> tw_lo, tw_hi, t1;
+  if (LOGN == 24) {
+    tw_lo = table(f, wf, 1, 4096);                       // forward tables; the kernel negates exponents for INV
+    tw_hi = table(f, h_powmod(wf, 4096, p), 1, 4096);
+    if (g_ntt3_t1) {                                     // mirrors ntt3_t1_kernel
+      t1.resize(n);
+      for (u64 i = 0; i < n; i++) {
+        u32 ex = (u32)((i >> 16) * (i & 0xFFFFu)) & 0xFFFFFFu;
+        if (INV) ex = (0u - ex) & 0xFFFFFFu;
+        t1[i] = f.mul_tw(tw_lo[ex & 4095u], tw_hi[ex >> 12]);
+      }
+    }
+  }
+  const u64 ninv = INV ? h_powmod(n % p, p - 2, p) : 1;
+  std::vector<u64> t2(65536);
+  const u64 w16 = h_powmod(w, n >> 16, p);
+  for (u32 i = 0; i < 65536; i++) t2[i] = f.to_tw(f.mul(field_pow(f, w16, (u64)((i >> 8) * (i & 255u))), ninv));
+  std::vector<u64> ws((size_t)batch << LOGN);
+  Ntt3Args A = {};
+  A.tw256 = tw256.data(); A.tw_lo = tw_lo.data(); A.tw_hi = tw_hi.data(); A.t2 = t2.data(); A.batch = batch;
+  A.t1 = t1.empty() ? nullptr : t1.data();
+  A.src_len = src_len; A.dst_len = dst_len;
+  A.src = src ? src : data; A.dst = ws.data();          // the flow of run_ntt3(): src → ws, ws in place, ws → data
+  if (LOGN == 24) {
+    run_pass3<F, 1, INV, LOGN, BOUNDED>(f, A);
+    A.src = ws.data();
+  }
+  run_pass3<F, 2, INV, LOGN, BOUNDED && LOGN == 16>(f, A);
+  A.src = ws.data(); A.dst = data; A.mul_src = mul; A.flags = mul ? NTT_FLAG_MUL : 0;
+  run_pass3<F, 3, INV, LOGN, BOUNDED>(f, A);
+  return 0;
+}
+
 }  // namespace
 
 
@@ -260,6 +315,49 @@ int emu_ntt(uint64_t p, uint64_t g, uint64_t* data, const uint64_t* mul, uint32_
   MontField f = make_mont(p, g, inverse != 0);
   return inverse ? run<MontField, true>(f, p, g, false, data, mul, log_n, batch, tile_cap, pref1, pref2)
                  : run<MontField, false>(f, p, g, false, data, mul, log_n, batch, tile_cap, pref1, pref2);
+}
+// Goldilocks (g = 7) 2^24- or 2^16-point transforms through the 256-point-tile kernel functions.
+int emu_ntt3(uint64_t* data, const uint64_t* mul, uint32_t log_n, uint32_t batch, int inverse, int t1_table) {
+  GoldilocksField f;
+  g_ntt3_t1 = t1_table;
+  if (log_n == 24)
+    return inverse ? run3<GoldilocksField, true, 24>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 24>(f, GL_P, 7, data, mul, batch);
+  if (log_n == 16)
+    return inverse ? run3<GoldilocksField, true, 16>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 16>(f, GL_P, 7, data, mul, batch);
+  return 1;
+}
+// one bounded 2^24 transform, as the polynomial product uses it: dst[0, dst_len) = NTT(src[0, src_len) zero-extended) [⊙ mul]
+int emu_ntt3_bounded(const uint64_t* src, uint64_t src_len, uint64_t* dst, uint64_t dst_len, const uint64_t* mul, int inverse) {
+  GoldilocksField f;
+  g_ntt3_t1 = 0;
+  return inverse ? run3<GoldilocksField, true, 24, true>(f, GL_P, 7, dst, mul, 1, src, src_len, dst_len)
+                 : run3<GoldilocksField, false, 24, true>(f, GL_P, 7, dst, mul, 1, src, src_len, dst_len);
+}
+// worst bank multiplicity of the three-pass tile layout over all accesses of all passes (1 = conflict-free)
+int emu_layout3_worst_conflict(void) {
+  int worst = 1;
+  auto account = [&](u32 (&w)[16]) {
+    int cnt[16] = {0};
+    for (int l = 0; l < 16; l++) cnt[w[l] & 15]++;
+    for (int k = 0; k < 16; k++) worst = cnt[k] > worst ? cnt[k] : worst;
+  };
+  std::vector<int> seen(N3_TILE_WORDS, 0);
+  for (u32 d1 = 0; d1 < 16; d1++) for (u32 d0 = 0; d0 < 16; d0++) for (u32 c = 0; c < 16; c++)
+    if (n3_word(d1, d0, c) >= N3_TILE_WORDS || seen[n3_word(d1, d0, c)]++) return -1;
+  for (int pass = 1; pass <= 3; pass++)
+    for (u32 hw = 0; hw < 16; hw++)      // half-warp = 16 consecutive groups
+      for (u32 q = 0; q < 16; q++) {
+        u32 w0[16], w1[16];
+        for (u32 l = 0; l < 16; l++) {
+          const u32 g = hw * 16 + l;
+          const u32 d0 = pass == 3 ? (g & 15u) : (g >> 4), c = pass == 3 ? (g >> 4) : (g & 15u);
+          w0[l] = n3_word(q, d0, c);                 // round-0 write of register q
+          w1[l] = n3_word(g >> 4, q, g & 15u);       // round-1 read of register q
+        }
+        account(w0);
+        account(w1);
+      }
+  return worst;
 }
 
 void emu_set_variant(int v) { g_variant = v; }

@@ -260,10 +260,11 @@ def test_pipelined_host_submit_wait():
 
 
 def test_opt_in_kernel_variants_agree_with_the_default():
-    """The switches read at ronk_ctx_create select alternative formulations of the same transform: the specialised
-    4096-point-per-tile kernel (RONK_FAST12=1: pairs, additive shared-memory layout, round 0 fed from HBM, n-word
-    inter-pass twiddle table) and the table form of the inter-pass twiddle under the generic kernel
-    (RONK_TW_TABLE=1).  Each must reproduce the default context's 2^24 and 2^23 transforms bit for bit, forward,
+    """The switches read at ronk_ctx_create select alternative formulations of the same transform: the default 2^24 path
+    is the three-pass kernel (ntt3_kernel.cuh, with programmatic dependent launch); RONK_NTT3=0 is the two-pass tile
+    kernel, optionally with the specialised 4096-point-per-tile kernel (RONK_FAST12=1: pairs, additive shared-memory
+    layout, round 0 fed from HBM) or the n-word inter-pass twiddle table (RONK_TW_TABLE=1); RONK_PDL=0 launches the
+    passes without overlap.  Each must reproduce the default context's 2^24 and 2^23 transforms bit for bit, forward,
     fused-multiply and inverse."""
     import os
     import torch
@@ -282,7 +283,7 @@ def test_opt_in_kernel_variants_agree_with_the_default():
         c0.sync()
         assert torch.equal(z, a[: 1 << lg])
         ref[lg] = (x, y)
-    for env in ({"RONK_FAST12": "1"}, {"RONK_TW_TABLE": "1"}):
+    for env in ({"RONK_NTT3": "0"}, {"RONK_NTT3": "0", "RONK_FAST12": "1"}, {"RONK_NTT3": "0", "RONK_TW_TABLE": "1"}, {"RONK_PDL": "0"}):
         old = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
         try:
@@ -303,3 +304,23 @@ def test_opt_in_kernel_variants_agree_with_the_default():
             c1.sync()
             assert torch.equal(x, ref[lg][0]) and torch.equal(y, ref[lg][1]) and torch.equal(z, a[: 1 << lg]), (env, lg)
         c1.close()
+
+
+def test_three_pass_batch_of_2_24():
+    """A batch of two 2^24-point transforms through the three-pass kernel equals the two transforms done singly
+    (which test_metric_size_2_24_bit_exact_and_properties pins against the oracle)."""
+    import torch
+    from ronkathon_b200 import ops
+    c = ctx()
+    a = ops.splitmix_fill(c, 2 << 24, 21, GL, "cuda")
+    one = [a[: 1 << 24].clone(), a[1 << 24:].clone()]
+    for t in one:
+        ops.ntt_(c, t, 24)
+    both = a.clone()
+    ops.ntt_(c, both, 24, batch=2)
+    c.sync()
+    assert torch.equal(both[: 1 << 24], one[0]) and torch.equal(both[1 << 24:], one[1])
+    ops.ntt_(c, both, 24, batch=2, inverse=True)
+    c.sync()
+    assert torch.equal(both, a)
+

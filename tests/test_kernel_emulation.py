@@ -23,7 +23,8 @@ def emu():
     hdr = os.path.join(HERE, "..", "ronkathon_b200", "csrc", "ntt_kernel.cuh")
     hdr2 = os.path.join(HERE, "..", "ronkathon_b200", "csrc", "field.cuh")
     hdr3 = os.path.join(HERE, "..", "ronkathon_b200", "csrc", "ntt12_kernel.cuh")
-    newest = max(os.path.getmtime(x) for x in (src, hdr, hdr2, hdr3))
+    hdr4 = os.path.join(HERE, "..", "ronkathon_b200", "csrc", "ntt3_kernel.cuh")
+    newest = max(os.path.getmtime(x) for x in (src, hdr, hdr2, hdr3, hdr4))
     if not os.path.exists(so) or os.path.getmtime(so) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src])
     lib = C.CDLL(so)
@@ -34,6 +35,8 @@ def emu():
     lib.emu_gl_w16.argtypes = [C.c_uint64, P64]
     lib.emu_swizzle_worst_conflict.argtypes = [C.c_uint32, C.c_uint32]
     lib.emu_fast12_tiles.restype = C.c_uint64
+    lib.emu_ntt3.argtypes = [P64, P64, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
+    lib.emu_ntt3_bounded.argtypes = [P64, C.c_uint64, P64, C.c_uint64, P64, C.c_int]
     return lib
 
 
@@ -259,3 +262,63 @@ def test_fast12_agrees_with_generic_kernel_and_fused_multiply(emu):
     assert np.array_equal(fast, slow)
     assert np.array_equal(fast, oracle.vec_mul(GL, oracle.ntt_fast(GL, a), b))
 
+
+# ---- the three-pass 2^24 transform (ntt3_kernel.cuh) --------------------------------------------------------
+def test_three_pass_tile_layout_is_conflict_free(emu):
+    assert emu.emu_layout3_worst_conflict() == 1
+
+
+@pytest.mark.parametrize("t1_table", [0, 1])
+def test_three_pass_2_24_matches_oracle_forward_fused_multiply_and_inverse(emu, t1_table):
+    """2^24 = 256·256·256: pass 1 (ω_n^(k1·m) twiddle stepped, or from the n-word table), pass 2 (64 Ki-entry table),
+    pass 3 (contiguous axis, natural-order output), the fused point-wise multiply of the last pass, and the inverse
+    (n^-1 in the pass-2 table) — the kernel's own functions on the CPU, against the oracle."""
+    a, b = oracle.splitmix(GL, 42, 1 << 24), oracle.splitmix(GL, 43, 1 << 24)
+    X = a.copy()
+    assert emu.emu_ntt3(_ptr(X), None, 24, 1, 0, t1_table) == 0
+    ref = oracle.ntt_fast(GL, a)
+    assert np.array_equal(X, ref)
+    if t1_table == 0:
+        Y = a.copy()
+        assert emu.emu_ntt3(_ptr(Y), _ptr(b), 24, 1, 0, 0) == 0
+        assert np.array_equal(Y, oracle.vec_mul(GL, ref, b))
+    assert emu.emu_ntt3(_ptr(X), None, 24, 1, 1, t1_table) == 0
+    assert np.array_equal(X, a)
+
+
+def test_two_pass_256_tiles_2_16_batch(emu):
+    """2^16 = 256·256 (BASELINE config 5's transform length) through the same tile functions, a batch of 5: forward
+    against the oracle per transform, fused multiply, inverse."""
+    n, batch = 1 << 16, 5
+    a = oracle.splitmix(GL, 9, n * batch)
+    m = oracle.splitmix(GL, 10, n * batch)
+    X = a.copy()
+    assert emu.emu_ntt3(_ptr(X), None, 16, batch, 0, 0) == 0
+    for b in range(batch):
+        assert np.array_equal(X[b * n:(b + 1) * n], oracle.ntt_fast(GL, a[b * n:(b + 1) * n])), b
+    Y = a.copy()
+    assert emu.emu_ntt3(_ptr(Y), _ptr(m), 16, batch, 0, 0) == 0
+    assert np.array_equal(Y, oracle.vec_mul(GL, X, m))
+    assert emu.emu_ntt3(_ptr(X), None, 16, batch, 1, 0) == 0
+    assert np.array_equal(X, a)
+
+
+def test_three_pass_bounded_source_and_destination(emu):
+    """The polynomial product's use of the 2^24 transform: the source is shorter than n (zero-extended inside the first
+    pass's loads), the destination buffer is shorter than n (the last pass stores dst[0, dst_len) only — the words
+    after it must stay untouched)."""
+    n = 1 << 24
+    src_len, dst_len = (1 << 23) + 12345, n - 54321
+    a = oracle.splitmix(GL, 77, src_len)
+    full = np.zeros(n, dtype=np.uint64)
+    full[:src_len] = a
+    ref = oracle.ntt_fast(GL, full)
+    guard = np.uint64(0xDEADBEEFCAFEF00D)
+    dst = np.full(dst_len + 1024, guard, dtype=np.uint64)
+    assert emu.emu_ntt3_bounded(_ptr(a), src_len, _ptr(dst), dst_len, None, 0) == 0
+    assert np.array_equal(dst[:dst_len], ref[:dst_len])
+    assert np.all(dst[dst_len:] == guard)
+    back = np.full(src_len + 64, guard, dtype=np.uint64)
+    assert emu.emu_ntt3_bounded(_ptr(ref), n, _ptr(back), src_len, None, 1) == 0
+    assert np.array_equal(back[:src_len], a)
+    assert np.all(back[src_len:] == guard)

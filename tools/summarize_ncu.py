@@ -45,8 +45,22 @@ def main(rep, out):
                     rd = float(r[i]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[units[i]]
                 if k == "dram__bytes_write.sum":
                     wr = float(r[i]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}[units[i]]
+        stalls = []
+        for i, h in enumerate(hdr):
+            if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and "not_issued" not in h:
+                try:
+                    v = float(r[i])
+                except ValueError:
+                    continue
+                if v > 0.05:
+                    stalls.append((v, h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")))
+        if stalls:
+            lines.append("   stall cycles per issued instruction: " + ", ".join(f"{n} {v:.2f}" for v, n in sorted(stalls, reverse=True)))
         import re
         m = re.search(r"ntt_tile_kernel<[^,]+, *(?:\(int\))?(\d), *(?:\(bool\))?(\d)", r[ki])
+        m3 = re.search(r"ntt3_kernel<[^,]+, *(?:\(int\))?(\d), *(?:\(bool\))?(\d)", r[ki])
+        if m3 and rd is not None:
+            traffic[("intt3_pass" if m3.group(2) == "1" else "ntt3_pass") + m3.group(1)] = rd + wr
         if m and rd is not None:
             nm = {"0": "single", "1": "pass1", "2": "pass2"}[m.group(1)]
             traffic[("intt_" if m.group(2) == "1" else "ntt_") + nm] = rd + wr
