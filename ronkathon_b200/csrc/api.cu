@@ -52,6 +52,7 @@ int ronk_ctx_create(ronk_ctx** out, int device, void* stream) {
   ctx->tune.tile_adapt = env_int("RONK_TILE_ADAPT", 1);
   ctx->tune.fast12 = env_int("RONK_FAST12", 0);
   ctx->tune.tw_table = env_int("RONK_TW_TABLE", ctx->tune.fast12 ? 1 : 0);  // the specialised pass 1 reads the table
+  ctx->tune.msm_coord = env_int("RONK_MSM_COORD", 1);
   ctx->tune.msm_hist = env_int("RONK_MSM_HIST", 1);
   ctx->tune.msm_split = env_int("RONK_MSM_SPLIT", 0);
   ctx->stream = (cudaStream_t)stream;
@@ -106,6 +107,7 @@ int ronk_ctx_destroy(ronk_ctx* ctx) {
   if (ctx->ws2) cudaFree(ctx->ws2);
   if (ctx->msm_ytab) cudaFree(ctx->msm_ytab);
   if (ctx->msm_done) cudaFree(ctx->msm_done);
+  if (ctx->msm_coord) cudaFree(ctx->msm_coord);
   if (ctx->d_flag) cudaFree(ctx->d_flag);
   if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
   delete ctx;

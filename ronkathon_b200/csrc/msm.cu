@@ -114,14 +114,10 @@ __global__ void __launch_bounds__(16 * MSM_FIN_LANES) msm_finish_kernel(const u3
 //   msm_hist_finish     one thread per bin: column sum mod 102, c·P by double-and-add with the reference's
 //                       addition law, CTA tree; the last CTA to finish reduces the CTA sums and writes result
 //                       and error flag straight into mapped pinned host memory (no memset / memcpy launches).
-constexpr u32 MSM_XS = Q101 * Q101;   // 10201 x values
-constexpr u32 MSM_BINS = 2 * MSM_XS;  // 20402
-constexpr u32 MSM_EXP = 102;          // group exponent of E(F_101²) ≅ (Z/102)²
+// (MSM_XS, MSM_BINS, MSM_EXP, y_bit, pt_bin: msm_curve.cuh)
 constexpr int MSM_HIST_THREADS = 1024;
 constexpr int MSM_FIN_THREADS = 256;   // bins per finishing CTA
 constexpr u32 MSM_FIN_GROUPS = 4;      // thread groups sharing the column sum of those bins (blockDim = 1024)
-
-RONK_DEV u32 y_bit(u32 y0, u32 y1) { return y0 ? (y0 > 50u) : (y1 > 50u); }
 
 // sq[idx(y²)] = y (either root), for every y in F_101²
 __global__ void msm_sqrt_table_kernel(uint16_t* sq) {
@@ -301,6 +297,151 @@ msm_hist_finish_kernel(const u32* __restrict__ partial, u32 sets, u32* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// kzg::commit in group coordinates (round 2, default).  E(F_101²) ≅ (Z/102)² (msm_curve.cuh, build_group_tables):
+// with P_i = a_i·G1 + b_i·G2,  Σ s_i·P_i = (Σ s_i a_i mod 102)·G1 + (Σ s_i b_i mod 102)·G2.  Per term: one 4-byte and
+// one 1-byte load (16 + 4 bytes per four terms on the vector path), the same validation as the histogram kernel (the
+// table entry carries the y of the bin's curve point: is_on_curve, curve/mod.rs:130-139), ONE shared-memory load and
+// two integer multiply-adds into registers — no atomics, no dependent point additions.  One launch: the last CTA to
+// finish (atomic counter) looks the result up in pttab and writes it, with the error flag, into mapped pinned host
+// memory.  Bound by HBM at 5 B/term once the 82 KB table per CTA is amortised.
+constexpr int MSM_COORD_THREADS = 1024;
+constexpr int MSM_COORD_U = 4;  // 16-byte point loads in flight per thread (16 terms)
+
+__device__ __forceinline__ void msm_coord_term(u32 w, u32 s, const u32* __restrict__ tab, u32& acc_a, u32& acc_b, bool& bad) {
+  if (s >= 17u) { bad = true; return; }                      // not an F17 residue
+  if (w == PT_INF) return;                                   // Infinity · s = Infinity
+  if (__vcmpgeu4(w, 0x65656565u)) { bad = true; return; }    // a coordinate ≥ 101
+  const u32 e = tab[pt_bin(w)];
+  if ((e & 0xFFFFu) != (w >> 16)) { bad = true; return; }    // not on y² = x³ + 3 (empty bins hold 0xFFFF)
+  acc_a += s * ((e >> 16) & 0xFFu);                          // s = 0 adds nothing: g1 * 0 = Infinity (curve/mod.rs:163-165)
+  acc_b += s * (e >> 24);
+}
+
+__global__ void __launch_bounds__(MSM_COORD_THREADS, 1)
+msm_coord_kernel(const u32* __restrict__ points, const uint8_t* __restrict__ scalars, size_t n, int vec,
+                 const u32* __restrict__ bintab_g, const u32* __restrict__ pttab, u32* __restrict__ gacc /*[0] counter, [1] Σa, [2] Σb*/,
+                 volatile u32* host /*[0] flag, [1] result*/) {
+  extern __shared__ __align__(16) u32 msm_smem[];
+  u32* tab = msm_smem;  // [MSM_BINS]
+  __shared__ u32 wsum[2][MSM_COORD_THREADS / 32];
+  const u32 t = threadIdx.x;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(bintab_g);  // MSM_BINS padded to a multiple of 4 words
+    uint4* dst = reinterpret_cast<uint4*>(tab);
+    for (u32 i = t; i < (MSM_BINS + 3) / 4; i += MSM_COORD_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  u32 acc_a = 0, acc_b = 0;
+  bool bad = false;
+  const size_t gthreads = (size_t)gridDim.x * MSM_COORD_THREADS, gtid = (size_t)blockIdx.x * MSM_COORD_THREADS + t;
+  size_t done = 0;  // terms [0, done) are covered by the vector loop
+  if (vec) {
+    const size_t quads = n >> 2;
+    const uint4* p4 = reinterpret_cast<const uint4*>(points);
+    const u32* s4 = reinterpret_cast<const u32*>(scalars);
+    u32 it = 0;
+    for (size_t q0 = gtid; q0 < quads; q0 += gthreads * MSM_COORD_U) {
+      uint4 w[MSM_COORD_U];
+      u32 s[MSM_COORD_U];
+#pragma unroll
+      for (int u = 0; u < MSM_COORD_U; u++) {
+        const size_t q = q0 + (size_t)u * gthreads;
+        if (q < quads) { w[u] = p4[q]; s[u] = s4[q]; }
+        else { w[u] = make_uint4(PT_INF, PT_INF, PT_INF, PT_INF); s[u] = 0u; }
+      }
+#pragma unroll
+      for (int u = 0; u < MSM_COORD_U; u++) {
+        msm_coord_term(w[u].x, s[u] & 0xFFu, tab, acc_a, acc_b, bad);
+        msm_coord_term(w[u].y, (s[u] >> 8) & 0xFFu, tab, acc_a, acc_b, bad);
+        msm_coord_term(w[u].z, (s[u] >> 16) & 0xFFu, tab, acc_a, acc_b, bad);
+        msm_coord_term(w[u].w, s[u] >> 24, tab, acc_a, acc_b, bad);
+      }
+      // 16 terms ≤ 16·16·101 per pass: fold long before 32 bits fill (any n)
+      if ((++it & 0x3FFFu) == 0u) { acc_a %= MSM_EXP; acc_b %= MSM_EXP; }
+    }
+    done = quads << 2;
+  }
+  {
+    u32 it = 0;
+    for (size_t i = done + gtid; i < n; i += gthreads) {
+      msm_coord_term(points[i], (u32)scalars[i], tab, acc_a, acc_b, bad);
+      if ((++it & 0xFFFFFu) == 0u) { acc_a %= MSM_EXP; acc_b %= MSM_EXP; }
+    }
+  }
+  if (bad) host[0] = 1u;
+  acc_a %= MSM_EXP;
+  acc_b %= MSM_EXP;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    acc_a += __shfl_down_sync(0xFFFFFFFFu, acc_a, off);
+    acc_b += __shfl_down_sync(0xFFFFFFFFu, acc_b, off);
+  }
+  if ((t & 31u) == 0) { wsum[0][t >> 5] = acc_a; wsum[1][t >> 5] = acc_b; }
+  __syncthreads();
+  if (t < 32) {
+    u32 a = wsum[0][t], b = wsum[1][t];  // MSM_COORD_THREADS / 32 = 32 warps
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      a += __shfl_down_sync(0xFFFFFFFFu, a, off);
+      b += __shfl_down_sync(0xFFFFFFFFu, b, off);
+    }
+    if (t == 0) {
+      atomicAdd(&gacc[1], a % MSM_EXP);
+      atomicAdd(&gacc[2], b % MSM_EXP);
+      __threadfence();  // the sums (and the flag store) before the arrival
+      if (atomicAdd(&gacc[0], 1u) == gridDim.x - 1) {
+        __threadfence();
+        const u32 sa = atomicExch(&gacc[1], 0u) % MSM_EXP, sb = atomicExch(&gacc[2], 0u) % MSM_EXP;  // self-cleaning
+        gacc[0] = 0u;
+        host[1] = pttab[MSM_EXP * sa + sb];
+      }
+    }
+  }
+}
+
+static int msm_coord_device(ronk_ctx* ctx, const uint8_t* points, size_t n_points, const uint8_t* scalars, size_t n_scalars,
+                            u32* h_result) {
+  if (!ctx || (n_scalars && (!points || !scalars))) return set_err(ctx, RONK_EINVAL, "null argument");
+  if (n_points < n_scalars) return set_err(ctx, RONK_EINVAL, "srs shorter than coefficients (kzg/setup.rs:53)");
+  if (((uintptr_t)points & 3) != 0) return set_err(ctx, RONK_EINVAL, "points must be 4-byte aligned");
+  if (n_scalars == 0) { *h_result = PT_INF; return RONK_OK; }   // empty sum = Infinity (curve/mod.rs:219-223)
+  constexpr size_t kTabWords = (MSM_BINS + 3) / 4 * 4;
+  constexpr size_t kSmem = kTabWords * sizeof(u32);
+  if (!ctx->msm_coord) {  // one-time per context: basis search + tables on the host (≈ 3·10⁴ affine additions)
+    std::vector<u32> tabs(kTabWords + MSM_EXP * MSM_EXP + 4, 0xFFFFFFFFu);
+    if (!build_group_tables(tabs.data(), tabs.data() + kTabWords)) return set_err(ctx, RONK_ECUDA, "internal: no basis of E(F_101^2) found");
+    tabs[kTabWords + MSM_EXP * MSM_EXP + 0] = tabs[kTabWords + MSM_EXP * MSM_EXP + 1] = tabs[kTabWords + MSM_EXP * MSM_EXP + 2] = 0u;
+    RONK_CUDA(ctx, cudaMalloc(&ctx->msm_coord, tabs.size() * sizeof(u32)));
+    RONK_CUDA(ctx, cudaMemcpyAsync(ctx->msm_coord, tabs.data(), tabs.size() * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // tabs is pageable and goes out of scope
+  }
+  RONK_TRY(ensure_smem_attr(ctx, msm_coord_kernel, (int)kSmem));
+  const u32* bintab = (const u32*)ctx->msm_coord;
+  const u32* pttab = bintab + kTabWords;
+  u32* gacc = (u32*)ctx->msm_coord + kTabWords + MSM_EXP * MSM_EXP;
+  // a CTA is worth its 82 KB table load once every thread sees ≥ 4 terms
+  size_t ctas = (n_scalars + (size_t)MSM_COORD_THREADS * 4 - 1) / ((size_t)MSM_COORD_THREADS * 4);
+  if (ctas > (size_t)ctx->sm_count) ctas = (size_t)ctx->sm_count;
+  if (ctas < 1) ctas = 1;
+  const int vec = (((uintptr_t)points & 15) == 0 && ((uintptr_t)scalars & 3) == 0) ? 1 : 0;
+  volatile u32* host = (volatile u32*)ctx->h_flag;  // mapped pinned: [0] = flag, [1] = result
+  host[0] = 0u;
+  host[1] = PT_INF;
+  u32* host_dev = nullptr;
+  RONK_CUDA(ctx, cudaHostGetDevicePointer((void**)&host_dev, (void*)ctx->h_flag, 0));
+  {
+    LaunchScope ls(ctx, "msm_coord");
+    msm_coord_kernel<<<(unsigned)ctas, MSM_COORD_THREADS, kSmem, ctx->stream>>>((const u32*)points, scalars, n_scalars, vec, bintab,
+                                                                                pttab, gacc, (volatile u32*)host_dev);
+  }
+  RONK_TRY(check_launch(ctx, "msm_coord_kernel"));
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (host[0]) return set_err(ctx, RONK_EINVAL, "off-curve point, non-canonical coordinate or scalar >= 17");
+  *h_result = host[1];
+  return RONK_OK;
+}
+
 // element-wise curve ops (host API support). op: 0 add, 1 neg, 2 scalar-mul by repeated addition
 __global__ void point_op_kernel(int op, const u32* a, const u32* b, const uint8_t* sc, u32* out, size_t n, int* flag) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -473,7 +614,8 @@ int ronk_msm_pluto_ext(ronk_ctx* ctx, const uint8_t* points, size_t n_points, co
   ronk::DeviceGuard _dg(ctx);
   if (!out) return set_err(ctx, RONK_EINVAL, "null argument");
   u32 res = PT_INF;
-  if (ctx && ctx->tune.msm_hist) RONK_TRY(msm_hist_device(ctx, points, n_points, scalars, n_scalars, &res));
+  if (ctx && ctx->tune.msm_coord) RONK_TRY(msm_coord_device(ctx, points, n_points, scalars, n_scalars, &res));
+  else if (ctx && ctx->tune.msm_hist) RONK_TRY(msm_hist_device(ctx, points, n_points, scalars, n_scalars, &res));
   else RONK_TRY(msm_device(ctx, points, n_points, scalars, n_scalars, nullptr, &res));
   unpack_to_bytes(res, out);
   return RONK_OK;

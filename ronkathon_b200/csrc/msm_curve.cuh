@@ -113,4 +113,92 @@ RONK_DEV void build_inv_table(uint8_t* tab, u32 tid, u32 nthr) {
   for (u32 a = tid; a < Q101; a += nthr) tab[a] = (uint8_t)(a ? fq_inv(a) : 0);
 }
 
+// ---- point bins (shared by the histogram and the group-coordinate commit kernels) ----
+//   bin(P) = 2·(x0 + 101·x1) + ybit(y),  ybit(y) = y0 ? (y0 > 50) : (y1 > 50)   (y and -y get different bits)
+constexpr u32 MSM_XS = Q101 * Q101;   // 10201 x values
+constexpr u32 MSM_BINS = 2 * MSM_XS;  // 20402
+constexpr u32 MSM_EXP = 102;          // group exponent of E(F_101²) ≅ (Z/102)²
+RONK_DEV u32 y_bit(u32 y0, u32 y1) { return y0 ? (y0 > 50u) : (y1 > 50u); }
+RONK_DEV u32 pt_bin(u32 w) { return 2u * ((w & 0xFF) + Q101 * ((w >> 8) & 0xFF)) + y_bit((w >> 16) & 0xFF, w >> 24); }
+
+// ---- group coordinates (host only; plan building for msm_coord_kernel, also compiled by tests/emu) ----
+// E(F_101²): y² = x³ + 3 has 102² points and exponent 102, i.e. E ≅ (Z/102)².  With a basis (G1, G2) every point is
+// a·G1 + b·G2 for exactly one (a, b) ∈ (Z/102)², and Σ s_i·P_i = (Σ s_i a_i)·G1 + (Σ s_i b_i)·G2: the whole commit is two
+// integer dot products mod 102 plus ONE table lookup — the same group element the reference's chain of affine
+// additions (curve/mod.rs:178-213) arrives at, because the addition law is associative and commutative.
+//   bintab[bin(P)] = y0 | y1 << 8 | a << 16 | b << 24   (0xFFFFFFFF: no curve point in the bin — doubles as is_on_curve)
+//   pttab[102 a + b] = packed a·G1 + b·G2                (PT_INF at 0)
+// The basis is found by search, deterministically (first points in x order that work), with the reference's own
+// addition law; injectivity of (a, b) → point is CHECKED while the table is filled, so a wrong basis cannot survive.
+// Returns false if no basis was found (cannot happen for this curve; the caller reports an internal error).
+inline bool build_group_tables(u32* bintab /*MSM_BINS*/, u32* pttab /*MSM_EXP²*/) {
+  // curve points in x order: sq[idx(y²)] = y
+  static const u32 kNone = 0xFFFFFFFFu;
+  u32* sq = new u32[MSM_XS];
+  for (u32 i = 0; i < MSM_XS; i++) sq[i] = kNone;
+  for (u32 i = 0; i < MSM_XS; i++) {
+    const Gf y = {i % Q101, i / Q101};
+    const Gf y2 = gf_mul(y, y);
+    u32& slot = sq[y2.c0 + Q101 * y2.c1];
+    if (slot == kNone) slot = i;  // the smaller of the two roots (deterministic)
+  }
+  u32* cand = new u32[2 * MSM_XS];
+  u32 ncand = 0;
+  for (u32 i = 0; i < MSM_XS; i++) {
+    const Gf x = {i % Q101, i / Q101};
+    const Gf rhs = gf_add(gf_mul(gf_mul(x, x), x), Gf{3, 0});
+    const u32 r = sq[rhs.c0 + Q101 * rhs.c1];
+    if (r == kNone) continue;
+    Pt p;
+    p.inf = false;
+    p.x = x;
+    p.y = {r % Q101, r / Q101};
+    cand[ncand++] = pt_pack(p);
+    const Gf ny = gf_neg(p.y);
+    if (!gf_eq(ny, p.y)) { p.y = ny; cand[ncand++] = pt_pack(p); }
+  }
+  delete[] sq;
+  auto order_is_102 = [](u32 w) {
+    u32 acc = w;
+    for (u32 k = 1; k < MSM_EXP; k++) {  // acc = k·w
+      if (acc == PT_INF) return false;
+      acc = pt_add_w(acc, w);
+    }
+    return acc == PT_INF;  // 102·w = O and no smaller multiple was
+  };
+  bool ok = false;
+  if (ncand == MSM_EXP * MSM_EXP - 1) {
+    u32 g1 = PT_INF;
+    u32 i1 = 0;
+    for (; i1 < ncand; i1++)
+      if (order_is_102(cand[i1])) { g1 = cand[i1]; break; }
+    for (u32 i2 = i1 + 1; g1 != PT_INF && i2 < ncand && !ok; i2++) {
+      const u32 g2 = cand[i2];
+      if (!order_is_102(g2)) continue;
+      for (u32 i = 0; i < MSM_BINS; i++) bintab[i] = kNone;
+      bool inj = true, seen_inf = false;
+      u32 row = PT_INF;  // a·G1
+      for (u32 a = 0; a < MSM_EXP && inj; a++) {
+        u32 cur = row;   // a·G1 + b·G2
+        for (u32 b = 0; b < MSM_EXP; b++) {
+          if (cur == PT_INF) {
+            if (seen_inf) { inj = false; break; }
+            seen_inf = true;
+          } else {
+            u32& e = bintab[pt_bin(cur)];
+            if (e != kNone) { inj = false; break; }
+            e = (cur >> 16) | (a << 16) | (b << 24);
+          }
+          pttab[MSM_EXP * a + b] = cur;
+          cur = pt_add_w(cur, g2);
+        }
+        row = pt_add_w(row, g1);
+      }
+      ok = inj;
+    }
+  }
+  delete[] cand;
+  return ok;
+}
+
 }  // namespace ronk

@@ -58,6 +58,7 @@ struct ronk_tune {
   int fast12 = 0;           // RONK_FAST12: the specialised 4096-point-per-tile kernel (ntt12_kernel.cuh) where it applies — opt-in:
                             // 20 % fewer instructions but slower on B200 (0.392 vs 0.379 ms); needs RONK_TW_TABLE=1 for pass 1
   int msm_split = 0;        // RONK_MSM_SPLIT: ≥ 2^22 terms: every other term to an L2-resident histogram (global RED)
+  int msm_coord = 1;        // RONK_MSM_COORD: kzg::commit in group coordinates (two dot products mod 102 + one lookup); 0 = the paths below
   int msm_hist = 1;         // RONK_MSM_HIST: kzg::commit through the point-indexed histogram (1) or the bucket kernels (0)
   int tw_table = 0;         // RONK_TW_TABLE: inter-pass twiddles from an n-word table (1) or stepped w ← w·ρ (0)
 };
@@ -87,6 +88,7 @@ struct ronk_ctx {
   void* dist = nullptr;      // ronk::DistState (dist.cu): communicator, peer mappings, staging — null until ronk_dist_init
   void* msm_ytab = nullptr;  // uint16_t[20402]: y of the curve point in each histogram bin (msm.cu), built on first use
   void* msm_done = nullptr;  // u32 completion counter of msm_hist_finish_kernel
+  void* msm_coord = nullptr; // msm_coord_kernel: bintab[20404] | pttab[10404] | counter, Σa, Σb (msm.cu), built on first use
   int* d_flag = nullptr;  // device error flag
   int* h_flag = nullptr;  // pinned host mirror: h_flag[0] = error flag, h_flag[1..31] = small results (msm.cu)
 };

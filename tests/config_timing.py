@@ -54,6 +54,14 @@ def main():
     torch.cuda.set_device(0)
     ctx = Context(0, torch.cuda.current_stream().cuda_stream)
     out = {}
+    only_msm = "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "msm"
+    if not only_msm:
+        ntt_configs(ctx, out)
+    msm_configs(ctx, out)
+    print(json.dumps(out))
+
+
+def ntt_configs(ctx, out):
     # config 2: one 2^20 transform
     n = 1 << 20
     a = oracle.splitmix(GL, 42, n)
@@ -98,6 +106,9 @@ def main():
         sweep[f"2^{lg}"] = round(timed(lambda: ops.ntt_(ctx, dd, lg)), 4)
         del dd
     out["single_transform_ms"] = sweep
+
+
+def msm_configs(ctx, out):
     for log_n in (10, 16, 20, 24):
         n = 1 << log_n
         pts, sc = msm_inputs(n)
@@ -127,7 +138,6 @@ def main():
         out[f"config4_msm_2^{log_n}"] = {"bit_exact": bool(ok), "call_ms": round(call_ms, 4),
                              "kernel_ms": {name: round(float(np.median(v)), 4) for name, v in k.items()},
                              "point_adds_per_s": n / (call_ms * 1e-3)}
-    print(json.dumps(out))
 
 
 if __name__ == "__main__":

@@ -60,4 +60,26 @@ void emu_bucket_combine(const uint8_t* buckets16, uint8_t* out) {
   unpack4(v[0], out);
 }
 
+// group-coordinate tables of msm_coord_kernel (build_group_tables, host plan code): bintab[MSM_BINS], pttab[102²];
+// returns 1 when a basis was found and (a, b) → a·G1 + b·G2 is injective
+int emu_group_tables(uint32_t* bintab, uint32_t* pttab) { return build_group_tables(bintab, pttab) ? 1 : 0; }
+// the per-term step of msm_coord_kernel and its final lookup, serially: Σ s_i·P_i through the tables.
+// returns 0 ok, 1 rejected term (the kernel's error flag)
+int emu_coord_commit(const uint32_t* bintab, const uint32_t* pttab, const uint8_t* points, const uint8_t* scalars, uint64_t n,
+                     uint8_t* out) {
+  u32 acc_a = 0, acc_b = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    const u32 w = pack4(points + 4 * i), s = scalars[i];
+    if (s >= 17u) return 1;
+    if (w == PT_INF) continue;
+    if ((w & 0xFF) >= Q101 || ((w >> 8) & 0xFF) >= Q101 || ((w >> 16) & 0xFF) >= Q101 || (w >> 24) >= Q101) return 1;
+    const u32 e = bintab[pt_bin(w)];
+    if ((e & 0xFFFFu) != (w >> 16)) return 1;
+    acc_a = (acc_a + s * ((e >> 16) & 0xFFu)) % MSM_EXP;
+    acc_b = (acc_b + s * (e >> 24)) % MSM_EXP;
+  }
+  unpack4(pttab[MSM_EXP * acc_a + acc_b], out);
+  return 0;
+}
+
 }  // extern "C"

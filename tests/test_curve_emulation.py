@@ -28,6 +28,11 @@ def emu():
     lib.emu_point_valid.argtypes = [PU8, PU8, C.c_uint64]
     lib.emu_gf_op.argtypes = [C.c_int, PU8, PU8, PU8, C.c_uint64]
     lib.emu_bucket_combine.argtypes = [PU8, PU8]
+    PU32 = C.POINTER(C.c_uint32)
+    lib.emu_group_tables.argtypes = [PU32, PU32]
+    lib.emu_group_tables.restype = C.c_int
+    lib.emu_coord_commit.argtypes = [PU32, PU32, PU8, PU8, C.c_uint64, PU8]
+    lib.emu_coord_commit.restype = C.c_int
     return lib
 
 
@@ -97,3 +102,85 @@ def test_scan_based_bucket_combination(emu):
         buf = np.frombuffer(b"".join(B), dtype=np.uint8).copy()
         emu.emu_bucket_combine(_p(buf), _p(out))
         assert bytes(out) == expect
+
+
+# ---- kzg::commit in group coordinates (msm_coord_kernel): the host-built tables and the per-term step ----------
+MSM_BINS, EXP = 20402, 102
+
+
+@pytest.fixture(scope="module")
+def group_tables(emu):
+    bintab = np.empty(MSM_BINS + 2, dtype=np.uint32)
+    pttab = np.empty(EXP * EXP, dtype=np.uint32)
+    PU32 = C.POINTER(C.c_uint32)
+    assert emu.emu_group_tables(bintab.ctypes.data_as(PU32), pttab.ctypes.data_as(PU32)) == 1
+    return bintab, pttab
+
+
+def _unpack(w):
+    w = int(w)
+    return bytes([w & 0xFF, (w >> 8) & 0xFF, (w >> 16) & 0xFF, w >> 24])
+
+
+def test_group_tables_are_a_bijection_onto_the_curve(group_tables):
+    """pttab enumerates Infinity + 10 403 distinct curve points, bintab is its inverse and carries the y of every bin's
+    point (the kernel's is_on_curve), and every bin without a curve point is marked empty."""
+    bintab, pttab = group_tables
+    assert int(pttab[0]) == 0xFFFFFFFF
+    pts = [_unpack(w) for w in pttab[1:]]
+    assert len(set(pts)) == EXP * EXP - 1 and b"\xff" * 4 not in pts
+    assert all(oracle.on_curve(P) for P in pts)
+    filled = 0
+    for k, w in enumerate(pttab):
+        if k == 0:
+            continue
+        P = _unpack(w)
+        ybit = (P[2] > 50) if P[2] else (P[3] > 50)
+        e = int(bintab[2 * (P[0] + 101 * P[1]) + int(ybit)])
+        assert e & 0xFFFF == P[2] | (P[3] << 8) and (e >> 16) & 0xFF == k // EXP and e >> 24 == k % EXP
+        filled += 1
+    assert filled == EXP * EXP - 1
+    assert int((bintab[:MSM_BINS] != 0xFFFFFFFF).sum()) == EXP * EXP - 1   # all other bins are empty
+
+
+def test_group_tables_are_a_homomorphism(group_tables):
+    """pttab[a][b] + pttab[c][d] == pttab[a+c][b+d] under the reference's addition law (oracle), incl. doubling,
+    inverse pairs and Infinity: the property the two dot products mod 102 rest on."""
+    _, pttab = group_tables
+    rng = np.random.default_rng(11)
+    idx = rng.integers(0, EXP, size=(3000, 4))
+    idx[:EXP, 2:] = idx[:EXP, :2]                       # doubling
+    idx[EXP:2 * EXP, 2:] = (-idx[EXP:2 * EXP, :2]) % EXP  # P + (-P)
+    idx[2 * EXP:2 * EXP + 50, :2] = 0                   # Infinity + Q
+    for a, b, c, d in idx:
+        got = oracle.point_add(_unpack(pttab[EXP * a + b]), _unpack(pttab[EXP * c + d]))
+        assert got == _unpack(pttab[EXP * ((a + c) % EXP) + (b + d) % EXP]), (a, b, c, d)
+    # exponent 102: the basis points have order exactly 102
+    for k in (EXP, 1):
+        P, acc = _unpack(pttab[k]), b"\xff" * 4
+        for m in range(1, EXP + 1):
+            acc = oracle.point_add(acc, P)
+            assert (acc == b"\xff" * 4) == (m == EXP)
+
+
+def test_coord_commit_matches_oracle_commit(emu, group_tables):
+    """Σ s_i·P_i through the tables == the oracle's kzg::commit (kzg/setup.rs:48-60) on arbitrary curve points with
+    Infinity and zero scalars mixed in; off-curve / non-canonical / scalar ≥ 17 terms are rejected."""
+    bintab, pttab = group_tables
+    PU32 = C.POINTER(C.c_uint32)
+    tb, tp = bintab.ctypes.data_as(PU32), pttab.ctypes.data_as(PU32)
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 5, 17, 200, 1500):
+        words = pttab[rng.integers(0, EXP * EXP, n)]
+        pts = np.frombuffer(b"".join(_unpack(w) for w in words), dtype=np.uint8).reshape(n, 4).copy()
+        sc = rng.integers(0, 17, n).astype(np.uint8)
+        out = np.empty(4, dtype=np.uint8)
+        assert emu.emu_coord_commit(tb, tp, _p(pts), _p(sc), n, _p(out)) == 0
+        assert bytes(out) == oracle.commit(sc, pts, fast=True)
+    pts = np.array([[36, 0, 0, 81]], dtype=np.uint8)      # off the curve (pluto_curve.rs:225-234)
+    out = np.empty(4, dtype=np.uint8)
+    assert emu.emu_coord_commit(tb, tp, _p(pts), _p(np.array([3], dtype=np.uint8)), 1, _p(out)) == 1
+    pts = np.array([[101, 0, 2, 0]], dtype=np.uint8)      # non-canonical coordinate
+    assert emu.emu_coord_commit(tb, tp, _p(pts), _p(np.array([3], dtype=np.uint8)), 1, _p(out)) == 1
+    pts = np.array([[1, 0, 2, 0]], dtype=np.uint8)        # scalar not an F17 residue
+    assert emu.emu_coord_commit(tb, tp, _p(pts), _p(np.array([17], dtype=np.uint8)), 1, _p(out)) == 1

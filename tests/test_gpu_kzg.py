@@ -123,3 +123,65 @@ def test_msm_rejects_bad_input():
     bad = pts.copy(); bad[3] = [101, 0, 2, 0]             # non-canonical coordinate
     with pytest.raises(RonkPanic):
         ops.msm(c, torch.from_numpy(bad).cuda(), torch.from_numpy(sc).cuda())
+
+
+def _full_group_points():
+    """The affine points of E(F_101²) with x1 ∈ {0, 1} and x0 ≡ 0 (mod 4), found by scanning — far outside the
+    17-torsion."""
+    out = []
+    for x0 in range(0, 101, 4):
+        for x1 in (0, 1):
+            for y0 in range(101):
+                for y1 in range(101):
+                    b = bytes([x0, x1, y0, y1])
+                    if oracle.on_curve(b):
+                        out.append(b)
+    rng = np.random.default_rng(8)                       # widen: sums of random pairs (the oracle's addition law)
+    for _ in range(3000):
+        i, j = rng.integers(0, len(out), 2)
+        q = oracle.point_add(out[i], out[j])
+        if q != b"\xff" * 4:
+            out.append(q)
+    return np.frombuffer(b"".join(out), dtype=np.uint8).copy().reshape(-1, 4)
+
+
+def test_commit_paths_agree_on_the_full_group_and_unaligned_input():
+    """kzg::commit three ways — group coordinates (default), point histogram (RONK_MSM_COORD=0), Pippenger buckets
+    (RONK_MSM_COORD=0 RONK_MSM_HIST=0) — on points of the whole curve group with Infinity and zero scalars mixed in,
+    against the oracle; sizes around the 4-term vector width and views that break the 16-byte alignment."""
+    import os
+    import torch
+    from ronkathon_b200 import Context, ops
+    base = _full_group_points()
+    rng = np.random.default_rng(21)
+    ctxs = {"coord": ctx()}
+    for name, env in (("hist", {"RONK_MSM_COORD": "0"}), ("buckets", {"RONK_MSM_COORD": "0", "RONK_MSM_HIST": "0"})):
+        os.environ.update(env)
+        try:
+            ctxs[name] = Context(0, torch.cuda.current_stream().cuda_stream)
+        finally:
+            for k in env:
+                os.environ.pop(k)
+    for n in (1, 3, 4, 5, 63, 1021, 65537, (1 << 18) + 7):
+        pts = base[rng.integers(0, len(base), n)].copy()
+        pts[rng.integers(0, n, max(1, n // 50))] = 0xFF            # Infinity terms
+        sc = rng.integers(0, 17, n).astype(np.uint8)
+        want = oracle.commit(sc, pts, fast=True)
+        P, S = torch.from_numpy(pts).cuda(), torch.from_numpy(sc).cuda()
+        for name, c in ctxs.items():
+            assert ops.msm(c, P, S) == want, (name, n)
+        if n > 8:   # drop 1 / 3 leading terms: the point pointer is no longer 16-byte aligned, the scalar pointer odd
+            for k in (1, 3):
+                assert ops.msm(ctxs["coord"], P[k:], S[k:]) == oracle.commit(sc[k:], pts[k:], fast=True), (n, k)
+    # repeated calls on one context: the kernel's global accumulators clean themselves
+    pts, sc = msm_inputs(5000)
+    P, S = torch.from_numpy(pts).cuda(), torch.from_numpy(sc).cuda()
+    want = oracle.commit(sc, pts, fast=True)
+    for _ in range(5):
+        assert ops.msm(ctxs["coord"], P, S) == want
+    # a rejected call leaves nothing behind either
+    bad = pts.copy(); bad[77] = [36, 0, 0, 81]
+    from ronkathon_b200 import RonkPanic
+    with pytest.raises(RonkPanic):
+        ops.msm(ctxs["coord"], torch.from_numpy(bad).cuda(), S)
+    assert ops.msm(ctxs["coord"], P, S) == want

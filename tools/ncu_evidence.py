@@ -48,5 +48,10 @@ if which in ("all", "msm"):
     P, S = torch.from_numpy(pts).cuda(), torch.from_numpy(sc).cuda()
     for _ in range(reps):
         ops.msm(ctx, P, S)
+if which == "msm24":
+    pts, sc = msm_terms(1 << 24)
+    P, S = torch.from_numpy(pts).cuda(), torch.from_numpy(sc).cuda()
+    for _ in range(reps):
+        ops.msm(ctx, P, S)
 ctx.sync()
 print("ok")
