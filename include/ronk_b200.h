@@ -207,9 +207,10 @@ int ronk_point_add_pluto_ext_host(ronk_ctx *ctx, const uint8_t *a, const uint8_t
 int ronk_point_neg_pluto_ext_host(ronk_ctx *ctx, const uint8_t *a, uint8_t *out, size_t n);
 int ronk_point_smul_pluto_ext_host(ronk_ctx *ctx, const uint8_t *a, const uint8_t *scalars, uint8_t *out, size_t n);
 /* kzg::commit — src/kzg/setup.rs:48-60: Σ points[i]·scalars[i] for i < n_scalars.  The group has
- * 102² points and exponent 102, so the sum is taken as a point-indexed histogram of the scalars (one
- * shared-memory atomicAdd per term) followed by c·P per occupied bin with the reference's addition law
- * (RONK_MSM_HIST=0 selects the round-1 Pippenger bucket kernels).  RONK_EINVAL if n_points < n_scalars (the reference's assert), if a scalar ≥ 17
+ * 102² points and exponent 102, i.e. E ≅ (Z/102)²: with a basis (G1, G2) found and checked on the host and
+ * P_i = a_i·G1 + b_i·G2 the sum is (Σ s_i a_i mod 102)·G1 + (Σ s_i b_i mod 102)·G2 — two integer dot products and one
+ * table lookup in ONE launch, the same affine point the reference's chain of additions yields (RONK_MSM_COORD=0
+ * selects the point-indexed histogram kernels, RONK_MSM_COORD=0 RONK_MSM_HIST=0 the round-1 Pippenger bucket kernels).  RONK_EINVAL if n_points < n_scalars (the reference's assert), if a scalar ≥ 17
  * or if a point is off-curve.  `points`/`scalars` are device pointers, `out` is a 4-byte HOST
  * buffer; synchronous. */
 int ronk_msm_pluto_ext(ronk_ctx *ctx, const uint8_t *points, size_t n_points, const uint8_t *scalars, size_t n_scalars, uint8_t out[4]);

@@ -306,65 +306,78 @@ msm_hist_finish_kernel(const u32* __restrict__ partial, u32 sets, u32* __restric
 // finish (atomic counter) looks the result up in pttab and writes it, with the error flag, into mapped pinned host
 // memory.  Bound by HBM at 5 B/term once the 82 KB table per CTA is amortised.
 constexpr int MSM_COORD_THREADS = 1024;
-constexpr int MSM_COORD_U = 4;  // 16-byte point loads in flight per thread (16 terms)
+constexpr int MSM_COORD_U = 2;  // 16-byte point loads per thread and batch; two batches (16 terms) are in flight
 
-__device__ __forceinline__ void msm_coord_term(u32 w, u32 s, const u32* __restrict__ tab, u32& acc_a, u32& acc_b, bool& bad) {
-  if (s >= 17u) { bad = true; return; }                      // not an F17 residue
-  if (w == PT_INF) return;                                   // Infinity · s = Infinity
-  if (__vcmpgeu4(w, 0x65656565u)) { bad = true; return; }    // a coordinate ≥ 101
-  const u32 e = tab[pt_bin(w)];
-  if ((e & 0xFFFFu) != (w >> 16)) { bad = true; return; }    // not on y² = x³ + 3 (empty bins hold 0xFFFF)
-  acc_a += s * ((e >> 16) & 0xFFu);                          // s = 0 adds nothing: g1 * 0 = Infinity (curve/mod.rs:163-165)
-  acc_b += s * (e >> 24);
+// Branch-free: a rejected term only raises `bad` (the call then fails and the sums are discarded).
+__device__ __forceinline__ void msm_coord_term(u32 w, u32 s, const u32* __restrict__ tab, u32& acc_a, u32& acc_b, u32& bad) {
+  // every coordinate < 101  ⟺  no byte of w or of w + 27·0x01010101 has bit 7 set (bytes < 128 cannot carry into their
+  // neighbour); Infinity (0xFFFFFFFF) is not canonical and contributes nothing
+  const bool canon = ((w | (w + 0x1B1B1B1Bu)) & 0x80808080u) == 0u;
+  const u32 e = canon ? tab[pt_bin(w)] : 0xFFFFFFFFu;
+  const bool on = canon && (e & 0xFFFFu) == (w >> 16);   // on y² = x³ + 3 (empty bins hold 0xFFFF in the y field)
+  bad |= (u32)(s >= 17u) | (u32)(!on && w != PT_INF);    // not an F17 residue / off the curve / non-canonical
+  const u32 sv = on ? s : 0u;                            // s = 0 adds nothing: g1 * 0 = Infinity (curve/mod.rs:163-165)
+  acc_a += sv * ((e >> 16) & 0xFFu);
+  acc_b += sv * (e >> 24);
+}
+
+struct MsmQuads {
+  uint4 w[MSM_COORD_U];
+  u32 s[MSM_COORD_U];
+};
+__device__ __forceinline__ void msm_coord_load(MsmQuads& b, const uint4* __restrict__ p4, const u32* __restrict__ s4, size_t q0,
+                                               size_t step, size_t quads) {
+#pragma unroll
+  for (int u = 0; u < MSM_COORD_U; u++) {
+    const size_t q = q0 + (size_t)u * step;
+    if (q < quads) { b.w[u] = p4[q]; b.s[u] = s4[q]; }
+    else { b.w[u] = make_uint4(PT_INF, PT_INF, PT_INF, PT_INF); b.s[u] = 0u; }
+  }
 }
 
 __global__ void __launch_bounds__(MSM_COORD_THREADS, 1)
 msm_coord_kernel(const u32* __restrict__ points, const uint8_t* __restrict__ scalars, size_t n, int vec,
-                 const u32* __restrict__ bintab_g, const u32* __restrict__ pttab, u32* __restrict__ gacc /*[0] counter, [1] Σa, [2] Σb*/,
-                 volatile u32* host /*[0] flag, [1] result*/) {
+                 const u32* __restrict__ bintab_g, const u32* __restrict__ pttab,
+                 unsigned long long* __restrict__ gacc /* arrivals << 48 | Σa << 24 | Σb */, volatile u32* host /*[0] flag, [1] result*/) {
   extern __shared__ __align__(16) u32 msm_smem[];
   u32* tab = msm_smem;  // [MSM_BINS]
   __shared__ u32 wsum[2][MSM_COORD_THREADS / 32];
   const u32 t = threadIdx.x;
+  const size_t gthreads = (size_t)gridDim.x * MSM_COORD_THREADS, gtid = (size_t)blockIdx.x * MSM_COORD_THREADS + t;
+  const size_t quads = vec ? (n >> 2) : 0;
+  const uint4* p4 = reinterpret_cast<const uint4*>(points);
+  const u32* s4 = reinterpret_cast<const u32*>(scalars);
+  const size_t step = gthreads * MSM_COORD_U;
+  // the first batch of terms is requested before the table: its HBM latency hides behind the 82 KB table copy
+  MsmQuads cur;
+  msm_coord_load(cur, p4, s4, gtid, gthreads, quads);
   {
     const uint4* src = reinterpret_cast<const uint4*>(bintab_g);  // MSM_BINS padded to a multiple of 4 words
     uint4* dst = reinterpret_cast<uint4*>(tab);
     for (u32 i = t; i < (MSM_BINS + 3) / 4; i += MSM_COORD_THREADS) dst[i] = src[i];
   }
   __syncthreads();
-  u32 acc_a = 0, acc_b = 0;
-  bool bad = false;
-  const size_t gthreads = (size_t)gridDim.x * MSM_COORD_THREADS, gtid = (size_t)blockIdx.x * MSM_COORD_THREADS + t;
-  size_t done = 0;  // terms [0, done) are covered by the vector loop
-  if (vec) {
-    const size_t quads = n >> 2;
-    const uint4* p4 = reinterpret_cast<const uint4*>(points);
-    const u32* s4 = reinterpret_cast<const u32*>(scalars);
+  u32 acc_a = 0, acc_b = 0, bad = 0;
+  {
     u32 it = 0;
-    for (size_t q0 = gtid; q0 < quads; q0 += gthreads * MSM_COORD_U) {
-      uint4 w[MSM_COORD_U];
-      u32 s[MSM_COORD_U];
+    for (size_t q0 = gtid; q0 < quads; q0 += step) {
+      MsmQuads nxt;
+      msm_coord_load(nxt, p4, s4, q0 + step, gthreads, quads);
 #pragma unroll
       for (int u = 0; u < MSM_COORD_U; u++) {
-        const size_t q = q0 + (size_t)u * gthreads;
-        if (q < quads) { w[u] = p4[q]; s[u] = s4[q]; }
-        else { w[u] = make_uint4(PT_INF, PT_INF, PT_INF, PT_INF); s[u] = 0u; }
+        msm_coord_term(cur.w[u].x, cur.s[u] & 0xFFu, tab, acc_a, acc_b, bad);
+        msm_coord_term(cur.w[u].y, (cur.s[u] >> 8) & 0xFFu, tab, acc_a, acc_b, bad);
+        msm_coord_term(cur.w[u].z, (cur.s[u] >> 16) & 0xFFu, tab, acc_a, acc_b, bad);
+        msm_coord_term(cur.w[u].w, cur.s[u] >> 24, tab, acc_a, acc_b, bad);
       }
-#pragma unroll
-      for (int u = 0; u < MSM_COORD_U; u++) {
-        msm_coord_term(w[u].x, s[u] & 0xFFu, tab, acc_a, acc_b, bad);
-        msm_coord_term(w[u].y, (s[u] >> 8) & 0xFFu, tab, acc_a, acc_b, bad);
-        msm_coord_term(w[u].z, (s[u] >> 16) & 0xFFu, tab, acc_a, acc_b, bad);
-        msm_coord_term(w[u].w, s[u] >> 24, tab, acc_a, acc_b, bad);
-      }
-      // 16 terms ≤ 16·16·101 per pass: fold long before 32 bits fill (any n)
+      cur = nxt;
+      // 8 terms ≤ 8·16·101 per pass: fold long before 32 bits fill (any n)
       if ((++it & 0x3FFFu) == 0u) { acc_a %= MSM_EXP; acc_b %= MSM_EXP; }
     }
-    done = quads << 2;
   }
   {
     u32 it = 0;
-    for (size_t i = done + gtid; i < n; i += gthreads) {
+    for (size_t i = (quads << 2) + gtid; i < n; i += gthreads) {  // tail of the vector path, or everything when unaligned
       msm_coord_term(points[i], (u32)scalars[i], tab, acc_a, acc_b, bad);
       if ((++it & 0xFFFFFu) == 0u) { acc_a %= MSM_EXP; acc_b %= MSM_EXP; }
     }
@@ -387,13 +400,13 @@ msm_coord_kernel(const u32* __restrict__ points, const uint8_t* __restrict__ sca
       b += __shfl_down_sync(0xFFFFFFFFu, b, off);
     }
     if (t == 0) {
-      atomicAdd(&gacc[1], a % MSM_EXP);
-      atomicAdd(&gacc[2], b % MSM_EXP);
-      __threadfence();  // the sums (and the flag store) before the arrival
-      if (atomicAdd(&gacc[0], 1u) == gridDim.x - 1) {
-        __threadfence();
-        const u32 sa = atomicExch(&gacc[1], 0u) % MSM_EXP, sb = atomicExch(&gacc[2], 0u) % MSM_EXP;  // self-cleaning
-        gacc[0] = 0u;
+      // ONE atomic per CTA carries both sums and the arrival; the CTA that sees all others' arrivals holds the totals
+      const unsigned long long mine = (1ull << 48) | ((unsigned long long)(a % MSM_EXP) << 24) | (unsigned long long)(b % MSM_EXP);
+      const unsigned long long old = atomicAdd(gacc, mine);
+      if ((old >> 48) == (unsigned long long)(gridDim.x - 1)) {
+        const unsigned long long tot = old + mine;
+        const u32 sa = (u32)((tot >> 24) & 0xFFFFFFull) % MSM_EXP, sb = (u32)(tot & 0xFFFFFFull) % MSM_EXP;
+        *gacc = 0ull;  // self-cleaning: the next call is ordered behind this kernel on the stream
         host[1] = pttab[MSM_EXP * sa + sb];
       }
     }
@@ -419,7 +432,8 @@ static int msm_coord_device(ronk_ctx* ctx, const uint8_t* points, size_t n_point
   RONK_TRY(ensure_smem_attr(ctx, msm_coord_kernel, (int)kSmem));
   const u32* bintab = (const u32*)ctx->msm_coord;
   const u32* pttab = bintab + kTabWords;
-  u32* gacc = (u32*)ctx->msm_coord + kTabWords + MSM_EXP * MSM_EXP;
+  static_assert((kTabWords + MSM_EXP * MSM_EXP) % 2 == 0, "the 64-bit accumulator must be 8-byte aligned");
+  unsigned long long* gacc = (unsigned long long*)((u32*)ctx->msm_coord + kTabWords + MSM_EXP * MSM_EXP);
   // a CTA is worth its 82 KB table load once every thread sees ≥ 4 terms
   size_t ctas = (n_scalars + (size_t)MSM_COORD_THREADS * 4 - 1) / ((size_t)MSM_COORD_THREADS * 4);
   if (ctas > (size_t)ctx->sm_count) ctas = (size_t)ctx->sm_count;

@@ -209,24 +209,135 @@ static int launch_tile(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tile
 }
 
 // ---- transforms as passes of 256-point tiles (ntt3_kernel.cuh): n = 2^24 (three passes) and n = 2^16 (two) -------
-template <class F, int PASS, bool INV, int LOGN, bool BOUNDED>
-static int launch3(ronk_ctx* ctx, const F& f, const Ntt3Args& A, const char* name, bool dependent) {
-  const unsigned tiles = A.batch * (LOGN == 24 ? 4096u : 16u);
+template <class F, int PASS, bool INV, int LOGN, bool BOUNDED, int NG>
+static int launch3_ng(ronk_ctx* ctx, const F& f, const Ntt3Args& A, const char* name, bool dependent, unsigned tiles) {
   LaunchScope ls(ctx, name);
   if (dependent && ctx->tune.ntt3_pdl && !ctx->prof) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(tiles);
-    cfg.blockDim = dim3(N3_THREADS);
+    cfg.blockDim = dim3(N3_THREADS * (2 / NG));
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RONK_CUDA(ctx, cudaLaunchKernelEx(&cfg, ntt3_kernel<F, PASS, INV, LOGN, BOUNDED>, f, A));
+    RONK_CUDA(ctx, cudaLaunchKernelEx(&cfg, ntt3_kernel<F, PASS, INV, LOGN, BOUNDED, NG>, f, A));
   } else {
-    ntt3_kernel<F, PASS, INV, LOGN, BOUNDED><<<tiles, N3_THREADS, 0, ctx->stream>>>(f, A);
+    ntt3_kernel<F, PASS, INV, LOGN, BOUNDED, NG><<<tiles, N3_THREADS * (2 / NG), 0, ctx->stream>>>(f, A);
   }
+  return RONK_OK;
+}
+template <class F, int PASS, bool INV, int LOGN, bool BOUNDED>
+static int launch3(ronk_ctx* ctx, const F& f, const Ntt3Args& A, const char* name, bool dependent) {
+  const unsigned tiles = A.batch * (LOGN == 24 ? 4096u : LOGN == 20 ? 256u : 16u);
+  // a grid that leaves most warp slots empty runs one radix-16 group per thread (256 threads per tile): a single
+  // 2^16- or 2^20-point transform is a chain of dependent carry chains per warp, and twice the warps halve it
+  if constexpr (LOGN != 24 && !BOUNDED) {
+    if (tiles < (unsigned)ctx->tune.ntt3_ng1_tiles * (unsigned)ctx->sm_count)
+      return launch3_ng<F, PASS, INV, LOGN, BOUNDED, 1>(ctx, f, A, name, dependent, tiles);
+  }
+  return launch3_ng<F, PASS, INV, LOGN, BOUNDED, 2>(ctx, f, A, name, dependent, tiles);
+}
+
+// pass C of the 2^20-point transform (ntt3c_kernel): one thread per (transform, k2)
+template <class F, bool INV>
+static int launch3c(ronk_ctx* ctx, const F& f, const Ntt3Args& A, const char* name) {
+  const unsigned blocks = (unsigned)((((u64)A.batch << 16) + N3C_THREADS - 1) / N3C_THREADS);
+  LaunchScope ls(ctx, name);
+  if (ctx->tune.ntt3_pdl && !ctx->prof) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(N3C_THREADS);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RONK_CUDA(ctx, cudaLaunchKernelEx(&cfg, ntt3c_kernel<F, INV>, f, A));
+  } else {
+    ntt3c_kernel<F, INV><<<blocks, N3C_THREADS, 0, ctx->stream>>>(f, A);
+  }
+  return RONK_OK;
+}
+
+// one-time tables of the 256-point-tile kernels for one direction: ω_256^x and the 64 Ki-entry ω_65536^(±k·j) [· n^-1]
+template <class F, bool INV>
+static int ntt3_tables(ronk_ctx* ctx, const F& f, NttPlan& pl, int log_n) {
+  const int d = INV ? 1 : 0;
+  if (pl.tw256[d]) return RONK_OK;
+  const u64 p = pl.p, n = (u64)1 << log_n;
+  u64 w = h_powmod(pl.g, (p - 1) / n, p);
+  if (INV) w = h_powmod(w, p - 2, p);
+  RONK_TRY(build_table(ctx, f, h_powmod(w, n >> 8, p), 1, &pl.tw256[d], 256));
+  RONK_CUDA(ctx, cudaMalloc((void**)&pl.t2[d], 65536 * sizeof(u64)));
+  const u64 ninv = INV ? h_powmod(n % p, p - 2, p) : 1;
+  {
+    LaunchScope ls(ctx, "ntt3_t2");
+    ntt3_t2_kernel<F><<<256, 256, 0, ctx->stream>>>(f, h_powmod(w, n >> 16, p), ninv, pl.t2[d]);
+  }
+  return check_launch(ctx, "ntt3_t2_kernel");
+}
+
+// Small batches of 2^16-point transforms in ONE launch: a 16-CTA thread-block cluster per transform, the pass-2 → pass-3
+// exchange through distributed shared memory (ntt16c_kernel).  In place, no workspace.  Returns RONK_OK with *done = false
+// when the device refuses the cluster shape (the caller then takes the two-launch path).
+template <class F, bool INV>
+static int run_ntt16_cluster(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, const u64* src, const u64* mul, u32 batch,
+                             bool* done) {
+  NttPlan& pl = const_cast<NttPlan&>(pl_c);
+  *done = false;
+  if (ctx->cluster16_state < 0) return RONK_OK;
+  RONK_TRY((ntt3_tables<F, INV>(ctx, f, pl, 16)));
+  constexpr size_t kSmem = (size_t)(N3_TILE_WORDS + N3_RECV_WORDS) * sizeof(u64);
+  auto kern = ntt16c_kernel<F, INV>;
+  const void* key = reinterpret_cast<const void*>(kern);
+  if (!ctx->smem_attr_done.count(key)) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->cluster16_state = -1;
+      return RONK_OK;
+    }
+    RONK_TRY(ensure_smem_attr(ctx, kern, (int)kSmem));
+  }
+  const int d = INV ? 1 : 0;
+  Ntt3Args A = {};
+  A.tw256 = pl.tw256[d];
+  A.t2 = pl.t2[d];
+  A.batch = batch;
+  A.src_len = A.dst_len = NTT_UNBOUNDED;
+  A.src = src;
+  A.dst = data;
+  A.mul_src = mul;
+  A.flags = mul ? NTT_FLAG_MUL : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(16u * batch);
+  cfg.blockDim = dim3(2 * N3_THREADS);
+  cfg.dynamicSmemBytes = kSmem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 16;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (ctx->cluster16_state == 0) {  // first use: can the device place a 16-CTA cluster of this footprint at all?
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) != cudaSuccess || clusters < 1) {
+      cudaGetLastError();
+      ctx->cluster16_state = -1;
+      return RONK_OK;
+    }
+    ctx->cluster16_state = 1;
+  }
+  {
+    LaunchScope ls(ctx, INV ? "intt16_cluster" : "ntt16_cluster");
+    RONK_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, f, A));
+  }
+  RONK_TRY(check_launch(ctx, "ntt16c_kernel"));
+  *done = true;
   return RONK_OK;
 }
 
@@ -238,19 +349,8 @@ static int run_ntt3(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, c
                     u64 src_len, u64 dst_len) {
   NttPlan& pl = const_cast<NttPlan&>(pl_c);
   const int d = INV ? 1 : 0;
-  const u64 p = pl.p, n = (u64)1 << LOGN;
-  if (!pl.tw256[d]) {  // one-time tables for this direction
-    u64 w = h_powmod(pl.g, (p - 1) / n, p);
-    if (INV) w = h_powmod(w, p - 2, p);
-    RONK_TRY(build_table(ctx, f, h_powmod(w, n >> 8, p), 1, &pl.tw256[d], 256));
-    RONK_CUDA(ctx, cudaMalloc((void**)&pl.t2[d], 65536 * sizeof(u64)));
-    const u64 ninv = INV ? h_powmod(n % p, p - 2, p) : 1;
-    {
-      LaunchScope ls(ctx, "ntt3_t2");
-      ntt3_t2_kernel<F><<<256, 256, 0, ctx->stream>>>(f, h_powmod(w, n >> 16, p), ninv, pl.t2[d]);
-    }
-    RONK_TRY(check_launch(ctx, "ntt3_t2_kernel"));
-  }
+  const u64 n = (u64)1 << LOGN;
+  RONK_TRY((ntt3_tables<F, INV>(ctx, f, pl, LOGN)));
   if (LOGN == 24 && ctx->tune.ntt3_t1 && !pl.t1[d]) {  // optional 128 MiB table of the pass-1 twiddles (no memory: stay stepped)
     if (cudaMalloc((void**)&pl.t1[d], n * sizeof(u64)) == cudaSuccess) {
       LaunchScope ls(ctx, "ntt3_t1");
@@ -263,6 +363,7 @@ static int run_ntt3(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, c
   }
   if (batch > (0x7FFFFFFFu >> 12)) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
   RONK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, ((size_t)batch << LOGN) * sizeof(u64)));
+  if (LOGN == 20 && (pl.log_n1 != 10 || !pl.tw_lo || !pl.tw2)) return set_err(ctx, RONK_ECUDA, "internal: unexpected 2^20 plan shape");
   Ntt3Args A = {};
   A.t1 = ctx->tune.ntt3_t1 ? pl.t1[d] : nullptr;
   A.tw256 = pl.tw256[d];
@@ -274,19 +375,37 @@ static int run_ntt3(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, c
   A.dst_len = dst_len;
   A.src = src;
   A.dst = (u64*)ctx->ws;
-  if (LOGN == 24) {
-    RONK_TRY((launch3<F, 1, INV, LOGN, BOUNDED>(ctx, f, A, INV ? "intt3_pass1" : "ntt3_pass1", false)));
-    RONK_TRY(check_launch(ctx, "ntt3 pass 1"));
+  if constexpr (LOGN == 20) {
+    // sixteen interleaved 2^16-point transforms + one radix-16 pass (ntt3_kernel.cuh): A1 src → data (identical views, so
+    // src == data is fine), A2 data → workspace, C workspace → data.  A.tw_hi = ω_n^(1024 y): the plan's 10 / 10 split.
+    A.dst = data;
+    RONK_TRY((launch3<F, 2, INV, 20, false>(ctx, f, A, INV ? "intt3_a1" : "ntt3_a1", false)));
+    RONK_TRY(check_launch(ctx, "ntt3 pass A1"));
+    A.src = data;
+    A.dst = (u64*)ctx->ws;
+    RONK_TRY((launch3<F, 1, INV, 20, false>(ctx, f, A, INV ? "intt3_a2" : "ntt3_a2", true)));
+    RONK_TRY(check_launch(ctx, "ntt3 pass A2"));
     A.src = (const u64*)ctx->ws;
+    A.dst = data;
+    A.mul_src = mul;
+    A.flags = mul ? NTT_FLAG_MUL : 0;
+    RONK_TRY((launch3c<F, INV>(ctx, f, A, INV ? "intt3_c" : "ntt3_c")));
+    return check_launch(ctx, "ntt3 pass C");
+  } else {
+    if constexpr (LOGN == 24) {
+      RONK_TRY((launch3<F, 1, INV, LOGN, BOUNDED>(ctx, f, A, INV ? "intt3_pass1" : "ntt3_pass1", false)));
+      RONK_TRY(check_launch(ctx, "ntt3 pass 1"));
+      A.src = (const u64*)ctx->ws;
+    }
+    RONK_TRY((launch3<F, 2, INV, LOGN, BOUNDED && LOGN == 16>(ctx, f, A, INV ? "intt3_pass2" : "ntt3_pass2", LOGN == 24)));
+    RONK_TRY(check_launch(ctx, "ntt3 pass 2"));
+    A.src = (const u64*)ctx->ws;
+    A.dst = data;
+    A.mul_src = mul;
+    A.flags = mul ? NTT_FLAG_MUL : 0;
+    RONK_TRY((launch3<F, 3, INV, LOGN, BOUNDED>(ctx, f, A, INV ? "intt3_pass3" : "ntt3_pass3", true)));
+    return check_launch(ctx, "ntt3 pass 3");
   }
-  RONK_TRY((launch3<F, 2, INV, LOGN, BOUNDED && LOGN == 16>(ctx, f, A, INV ? "intt3_pass2" : "ntt3_pass2", LOGN == 24)));
-  RONK_TRY(check_launch(ctx, "ntt3 pass 2"));
-  A.src = (const u64*)ctx->ws;
-  A.dst = data;
-  A.mul_src = mul;
-  A.flags = mul ? NTT_FLAG_MUL : 0;
-  RONK_TRY((launch3<F, 3, INV, LOGN, BOUNDED>(ctx, f, A, INV ? "intt3_pass3" : "ntt3_pass3", true)));
-  return check_launch(ctx, "ntt3 pass 3");
 }
 
 // src == nullptr: in place.  Otherwise (batch == 1) the transform reads src[0, src_len) zero-extended to n
@@ -318,6 +437,12 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
       // 2^16: worth it once the grid fills the GPU (16 tiles per transform); single transforms stay launch-bound
       if (log_n == 24 && !bounded) return run_ntt3<F, INV, 24, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
       if (log_n == 24 && batch == 1) return run_ntt3<F, INV, 24, true>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
+      if (log_n == 20 && !bounded && ctx->tune.ntt3_20) return run_ntt3<F, INV, 20, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
+      if (log_n == 16 && !bounded && batch <= (u32)ctx->tune.ntt16_cluster_max_batch) {
+        bool done = false;
+        RONK_TRY((run_ntt16_cluster<F, INV>(ctx, f, pl, data, src, mul, batch, &done)));
+        if (done) return RONK_OK;
+      }
       if (log_n == 16 && !bounded && batch >= (u32)ctx->tune.ntt3_min_batch16)
         return run_ntt3<F, INV, 16, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
     }

@@ -24,6 +24,24 @@
 // HBM at < 20 % of its peak, so the bytes are there to spend.  General multiplications per element: 3·15/16 (inner) + 2
 // (pass 1: stepped ω_n^(k1·m), apply) + 1 (pass 2: 64 Ki-entry table, L2-resident) = 5.8, as in the two-pass kernel.
 //
+// n = 2^20 (BASELINE config 2) reuses the two tile passes on SIXTEEN INTERLEAVED 2^16-point transforms and adds one
+// register-only radix-16 pass.  With j = j1 + 16·(256 j2h + j2l) and k = 65536 k1 + k2l + 256 k2h:
+//
+//   pass A1 (PASS 2 code)  T[j1, k2l, j2l] = ( Σ_j2h ω_256^(j2h k2l) a[j1 + 16·(256 j2h + j2l)] ) · ω_65536^(j2l k2l)   src → data
+//   pass A2 (PASS 1 code)  Y[j1, k2]       = ( Σ_j2l ω_256^(j2l k2h) T[j1, k2l, j2l] ) · ω_n^(j1·k2)                     data → workspace
+//   pass C  (ntt3c_kernel) X[65536 k1 + k2] = Σ_j1 ω_16^(j1 k1) Y[j1, k2]                                               workspace → data
+//
+// The sixteen columns of a tile are the sixteen interleaved transforms (j1), so every global access is again a full
+// 128-byte line; the twiddle of A1 is constant along a row, that of A2 is stepped like pass 1 of the 2^24 transform.
+//
+// ONE LAUNCH for small batches of 2^16-point transforms (ntt16c_kernel): the sixteen tiles of a transform are the sixteen
+// CTAs of a thread-block cluster.  CTA s runs pass 2 on tile s and writes output (k1 = 16 q' + b, j2) straight into the
+// shared memory of CTA q' — the one that runs pass 3 on columns k1 ∈ [16 q', 16 q' + 16) — through distributed shared
+// memory; after a cluster barrier every CTA runs pass 3 out of its own receive buffer.  The 512 KB intermediate never
+// leaves the SMs, the second launch disappears, and the transform is in place without a workspace (every input is in
+// shared memory before the first output is stored).  A cluster holds 68 KB × 16 of shared memory, so full grids keep
+// the two-launch form (six CTAs per SM); this is the latency path.
+//
 // Tile index e = (d1 << 8) | (d0 << 4) | c  (transform index i = 16·d1 + d0, column c); shared-memory word
 // word(e) = 272·d1 + 17·d0 + c: additive (every access is [R + imm]) and conflict-free for lanes that differ in c
 // (passes 1, 2 and every round-1 read) as well as for lanes that differ in d0 (round-0 writes of pass 3, whose
@@ -38,7 +56,11 @@ namespace ronk {
 #ifndef RONK_NTT3_UNROLL_GROUPS
 #define RONK_NTT3_UNROLL_GROUPS 1
 #endif
-constexpr u32 N3_THREADS = 128;
+#ifndef RONK_NTT3_MINB
+#define RONK_NTT3_MINB 6   // CTAs per SM the register budget is set for (6 × 35 KB is also the shared-memory limit)
+#endif
+constexpr u32 N3_THREADS = 128;   // NG = 2 groups per thread (full grids); NG = 1: 256 threads, one group each — twice
+                                  // the warps per tile for grids that do not fill the GPU (single 2^16 / 2^20 transforms)
 constexpr u32 N3_TILE_WORDS = 16 * 272;  // 4352 words = 34 816 B
 RONK_HD constexpr u32 n3_word(u32 d1, u32 d0, u32 c) { return 272u * d1 + 17u * d0 + c; }
 RONK_HD constexpr u32 n3_br4(int j) { return (u32)(((j & 1) << 3) | ((j & 2) << 1) | ((j & 4) >> 1) | ((j & 8) >> 3)); }
@@ -61,14 +83,14 @@ struct Ntt3Args {
 // ---- round 0: 16 elements per group straight from global memory ----
 // PASS 1, 2: group g ↔ (d0 = g >> 4, c = g & 15): element q is row i = 16 q + d0 of the tile, column c.
 // PASS 3:    group g ↔ (col = g >> 4, d0 = g & 15): element q is i = 16 q + d0 of column col (i is the contiguous axis).
-template <class F, int PASS, bool INV, bool BOUNDED = false>
+template <class F, int PASS, bool INV, bool BOUNDED = false, int NG = 2>
 RONK_DEV void n3_round0(const F& f, u64* smem, const Ntt3Args& A, u64 tile_base, u64 row_stride, u64 col_stride, u32 tid) {
 #if RONK_NTT3_UNROLL_GROUPS == 1
 #pragma unroll 1
 #else
 #pragma unroll
 #endif
-  for (int h = 0; h < 2; h++) {
+  for (int h = 0; h < NG; h++) {
     const u32 g = tid + (u32)h * N3_THREADS;
     const u32 d0 = (PASS == 3) ? (g & 15u) : (g >> 4), c = (PASS == 3) ? (g >> 4) : (g & 15u);
     const u64* p = A.src + tile_base + (u64)d0 * row_stride + (u64)c * col_stride;
@@ -94,14 +116,16 @@ RONK_DEV void n3_round0(const F& f, u64* smem, const Ntt3Args& A, u64 tile_base,
 // ---- round 1 + inter-pass twiddle + stores ----
 // group g ↔ (d1 = g >> 4, c = g & 15).  Register q is tile position d0 = q, i.e. output k = bitrev8(16 d1 + q) =
 // 16·bitrev4(q) + bitrev4(d1); it goes to row k of the output view, column c.
-template <class F, int PASS, bool INV, bool BOUNDED = false>
+template <class F, int PASS, bool INV, bool BOUNDED = false, int LOGN = 24, int NG = 2>
 RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile_base, u64 row_stride, u32 m_base, u32 tid) {
+  constexpr u32 LO = (LOGN == 20) ? 10u : 12u;            // two-level twiddle tables: ω_n^x, x < 2^LO, and ω_n^(2^LO·y)
+  constexpr u32 EMASK = (LOGN == 20) ? 0xFFFFFu : 0xFFFFFFu;  // exponents mod n
 #if RONK_NTT3_UNROLL_GROUPS == 1
 #pragma unroll 1
 #else
 #pragma unroll
 #endif
-  for (int h = 0; h < 2; h++) {
+  for (int h = 0; h < NG; h++) {
     const u32 g = tid + (u32)h * N3_THREADS;
     const u32 d1 = g >> 4, c = g & 15u;
     const u64* s = smem + n3_word(d1, 0, c);
@@ -111,7 +135,7 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
     radix_network<4, INV>(f, x);
     const u32 b = bitrev(d1, 4);
     u64* o = A.dst + tile_base + (u64)b * row_stride + c;   // row k = 16 q' + b, q' = bitrev4(register index)
-    if (PASS == 1 && A.t1) {
+    if (PASS == 1 && LOGN == 24 && A.t1) {
       // ω_n^(±k1·m) from the n-word table [k1][m]: the same offsets as the stores, one coalesced load each
       const u64* t = A.t1 + ((u64)b << 16) + m_base + c;
       u64 w[16];
@@ -121,11 +145,12 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
       for (int qp = 0; qp < 16; qp++) o[(u64)qp * 16u * row_stride] = f.mul_tw(x[n3_br4(qp)], w[qp]);
     } else if (PASS == 1) {
       // ω_n^(±k1·m), m = 256 j2 + j3 (this thread's column), k1 = 16 q' + b: stepped over q' with ρ = ω_n^(±16 m)
+      // 2^20 (pass A2): ω_n^(j1·k2), j1 = c (this thread's column), k2 = m_base + 256·(16 q' + b): ρ = ω_n^(4096 c)
       const u32 m = m_base + c;
-      u32 ex0 = m * b, exd = m << 4;
-      if (INV) { ex0 = (0u - ex0) & 0xFFFFFFu; exd = (0u - exd) & 0xFFFFFFu; }
-      u64 w = f.mul_tw(ld_tw(A.tw_lo + (ex0 & 4095u)), ld_tw(A.tw_hi + (ex0 >> 12)));
-      const u64 rho = f.mul_tw(ld_tw(A.tw_lo + (exd & 4095u)), ld_tw(A.tw_hi + (exd >> 12)));
+      u32 ex0 = (LOGN == 20) ? c * (m_base + 256u * b) : m * b, exd = (LOGN == 20) ? (c << 12) : (m << 4);
+      if (INV) { ex0 = (0u - ex0) & EMASK; exd = (0u - exd) & EMASK; }
+      u64 w = f.mul_tw(ld_tw(A.tw_lo + (ex0 & ((1u << LO) - 1u))), ld_tw(A.tw_hi + (ex0 >> LO)));
+      const u64 rho = f.mul_tw(ld_tw(A.tw_lo + (exd & ((1u << LO) - 1u))), ld_tw(A.tw_hi + (exd >> LO)));
 #pragma unroll
       for (int qp = 0; qp < 16; qp++) {
         o[(u64)qp * 16u * row_stride] = f.mul_tw(x[n3_br4(qp)], w);
@@ -133,7 +158,8 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
       }
     } else if (PASS == 2) {
       // ω_65536^(±k2·j3) from the 64 Ki-entry table [k2][j3]; m_base = first j3 of the tile
-      const u64* t = A.t2 + ((u64)b << 8) + m_base + c;
+      // 2^20 (pass A1): ω_65536^(k2l·j2l) with j2l = m_base the same for all sixteen columns
+      const u64* t = A.t2 + ((u64)b << 8) + m_base + (LOGN == 20 ? 0u : c);
       u64 w[16];
 #pragma unroll
       for (int qp = 0; qp < 16; qp++) w[qp] = ld_tw(t + ((u64)qp << 12));
@@ -155,6 +181,34 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
           if (!BOUNDED || idx0 + (u64)qp * 16u * row_stride < A.dst_len) o[(u64)qp * 16u * row_stride] = x[n3_br4(qp)];
       }
     }
+  }
+}
+
+// ---- round 1 of pass 2 inside a cluster: twiddle as PASS 2 (LOGN = 16), stores into the pass-3 CTAs' receive buffers ----
+// receive buffer of CTA t: R[col][i] = A2[k1 = 16 t + col][j2 = i] at word col·N3_RECV_STRIDE + i — exactly the view
+// n3_round0<PASS 3> reads with row stride 1 and column stride N3_RECV_STRIDE.  Both the stores (16 lanes = 16 consecutive
+// j2 of one column) and those reads (16 lanes = 16 consecutive i) are 128-byte runs: conflict-free.
+constexpr u32 N3_RECV_STRIDE = 256;
+constexpr u32 N3_RECV_WORDS = 16 * N3_RECV_STRIDE;
+template <class F, bool INV, int NG, class Remote>
+RONK_DEV void n3_round1_cluster(const F& f, const u64* smem, const Ntt3Args& A, u32 s_tile, u32 tid, const Remote& remote) {
+#pragma unroll 1
+  for (int h = 0; h < NG; h++) {
+    const u32 g = tid + (u32)h * N3_THREADS;
+    const u32 d1 = g >> 4, c = g & 15u;
+    const u64* s = smem + n3_word(d1, 0, c);
+    u64 x[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) x[q] = s[n3_word(0, (u32)q, 0)];
+    radix_network<4, INV>(f, x);
+    const u32 b = bitrev(d1, 4);
+    const u32 j2 = 16u * s_tile + c;
+    const u64* t = A.t2 + ((u64)b << 8) + j2;   // ω_65536^(±k1·j2) [· n^-1], k1 = 16 q' + b
+    u64 w[16];
+#pragma unroll
+    for (int qp = 0; qp < 16; qp++) w[qp] = ld_tw(t + ((u64)qp << 12));
+#pragma unroll
+    for (int qp = 0; qp < 16; qp++) remote((u32)qp)[b * N3_RECV_STRIDE + j2] = f.mul_tw(x[n3_br4(qp)], w[qp]);
   }
 }
 
@@ -186,6 +240,22 @@ RONK_DEV void n3_tile_geometry(u32 tile, u64* in_base, u64* in_row, u64* in_col,
     }
     return;
   }
+  if (LOGN == 20) {   // 256 tiles per transform in both passes; the 16 columns are the interleaved transforms j1
+    const u64 b = tile >> 8;
+    const u32 t = tile & 255u;
+    *in_col = 1;
+    *m_base = t;
+    *out_base = (b << 20) + 16u * t;
+    *out_row = 4096;
+    if (PASS == 2) {      // A1: t = j2l, rows j2h → k2l, in and out views identical
+      *in_base = *out_base;
+      *in_row = 4096;
+    } else {              // A2: t = k2l, rows j2l (one contiguous 4096-word block) → rows k2h of the natural-order view
+      *in_base = (b << 20) + 4096u * t;
+      *in_row = 16;
+    }
+    return;
+  }
   const u64 b = tile >> 12;
   const u32 hi = (tile >> 4) & 255u, lo = tile & 15u;
   if (PASS == 1) {        // hi = j2, lo = s
@@ -208,9 +278,28 @@ RONK_DEV void n3_tile_geometry(u32 tile, u64* in_base, u64* in_row, u64* in_col,
   }
 }
 
+// pass C body for one (transform b, k2): register q of the DIF network holds output k1 = bitrev4(q)
+template <class F, bool INV>
+RONK_DEV void n3c_point(const F& f, const Ntt3Args& A, u64 b, u64 k2) {
+  const u64* p = A.src + (b << 20) + 16u * k2;
+  u64 x[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) x[q] = p[q];
+  radix_network<4, INV>(f, x);
+  u64* o = A.dst + (b << 20) + k2;
+  if (A.flags & NTT_FLAG_MUL) {
+    const u64* mp = A.mul_src + (b << 20) + k2;
+#pragma unroll
+    for (int q = 0; q < 16; q++) o[(u64)n3_br4(q) << 16] = f.mul(x[q], mp[(u64)n3_br4(q) << 16]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 16; q++) o[(u64)n3_br4(q) << 16] = x[q];
+  }
+}
+
 #if defined(__CUDACC__)
-template <class F, int PASS, bool INV, int LOGN, bool BOUNDED>
-__global__ void __launch_bounds__(N3_THREADS, 6) ntt3_kernel(const F f, const Ntt3Args A) {
+template <class F, int PASS, bool INV, int LOGN, bool BOUNDED, int NG = 2>
+__global__ void __launch_bounds__(N3_THREADS * (2 / NG), RONK_NTT3_MINB / (2 / NG)) ntt3_kernel(const F f, const Ntt3Args A) {
   __shared__ u64 smem[N3_TILE_WORDS];
   const u32 tid = threadIdx.x;
   u64 in_base, in_row, in_col, out_base, out_row;
@@ -220,9 +309,57 @@ __global__ void __launch_bounds__(N3_THREADS, 6) ntt3_kernel(const F f, const Nt
   // not touch the predecessor's output before griddepcontrol.wait (no-ops without the launch attribute)
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  n3_round0<F, PASS, INV, BOUNDED && PASS == (LOGN == 24 ? 1 : 2)>(f, smem, A, in_base, in_row, in_col, tid);  // src_len: first pass only
+  n3_round0<F, PASS, INV, BOUNDED && PASS == (LOGN == 24 ? 1 : 2), NG>(f, smem, A, in_base, in_row, in_col, tid);  // src_len: first pass only
   __syncthreads();
-  n3_round1<F, PASS, INV, BOUNDED>(f, smem, A, out_base, out_row, m_base, tid);
+  n3_round1<F, PASS, INV, BOUNDED, LOGN, NG>(f, smem, A, out_base, out_row, m_base, tid);
+}
+
+// One 2^16-point transform per 16-CTA cluster, in place (see the header comment).  256 threads, one group each.
+struct N3ClusterRemote {
+  u64* recv;
+  __device__ __forceinline__ u64* operator()(u32 rank) const {
+    u64* r;   // mapa: the same shared-memory offset in CTA `rank` of this cluster (generic address)
+    asm("mapa.u64 %0, %1, %2;" : "=l"(r) : "l"(recv), "r"(rank));
+    return r;
+  }
+};
+template <class F, bool INV>
+__global__ void __launch_bounds__(2 * N3_THREADS, 3) ntt16c_kernel(const F f, const Ntt3Args A) {
+  extern __shared__ __align__(16) u64 n3_dyn[];
+  u64* tile = n3_dyn;
+  u64* recv = n3_dyn + N3_TILE_WORDS;
+  const u32 tid = threadIdx.x;
+  u32 rank;
+  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  u64 in_base, in_row, in_col, out_base, out_row;
+  u32 m_base;
+  n3_tile_geometry<2, 16>(blockIdx.x, &in_base, &in_row, &in_col, &out_base, &out_row, &m_base);
+  n3_round0<F, 2, INV, false, 1>(f, tile, A, in_base, in_row, in_col, tid);
+  __syncthreads();
+  // every CTA of the cluster is running (its receive buffer exists) and has its inputs in shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  n3_round1_cluster<F, INV, 1>(f, tile, A, rank, tid, N3ClusterRemote{recv});
+  // all sixteen CTAs' stores into this CTA's receive buffer have landed
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  Ntt3Args B = A;
+  B.src = recv;
+  n3_round0<F, 3, INV, false, 1>(f, tile, B, 0, 1, N3_RECV_STRIDE, tid);
+  __syncthreads();
+  n3_tile_geometry<3, 16>(blockIdx.x, &in_base, &in_row, &in_col, &out_base, &out_row, &m_base);
+  n3_round1<F, 3, INV, false, 16, 1>(f, tile, A, out_base, out_row, m_base, tid);
+}
+
+// pass C of the 2^20-point transform: one thread per (transform, k2) — sixteen contiguous words in, a radix-16 network in
+// registers (no twiddles: ω_16 is a power of two), sixteen stores at stride 65536, coalesced across the warp.
+constexpr u32 N3C_THREADS = 128;
+template <class F, bool INV>
+__global__ void __launch_bounds__(N3C_THREADS) ntt3c_kernel(const F f, const Ntt3Args A) {
+  const u64 i = (u64)blockIdx.x * N3C_THREADS + threadIdx.x;   // < batch · 65536
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (i >= ((u64)A.batch << 16)) return;
+  const u64 b = i >> 16, k2 = i & 0xFFFFu;
+  n3c_point<F, INV>(f, A, b, k2);
 }
 
 // T1[k1][m] = ω_n^(±k1·m), k1 < 256, m < 65536 (twiddle form), from the two-level tables

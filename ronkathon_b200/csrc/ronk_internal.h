@@ -47,6 +47,10 @@ struct NttPlan {
 // Tuning switches, read from the environment ONCE at ronk_ctx_create (never on the launch path).
 struct ronk_tune {
   int ntt3_min_batch16 = 1; // RONK_NTT3_MIN_BATCH16: smallest batch of 2^16-point transforms that takes the 256-point-tile kernels
+  int ntt16_cluster_max_batch = 8;  // RONK_NTT16_CLUSTER_MAX_BATCH: up to this many 2^16-point transforms go through ntt16c_kernel
+                                    // (one launch, 16-CTA cluster per transform, DSMEM exchange); 0 = never
+  int ntt3_ng1_tiles = 3;   // RONK_NTT3_NG1_TILES: grids below this many tiles per SM run one group per thread (256 threads per tile)
+  int ntt3_20 = 1;          // RONK_NTT3_20: 2^20-point transforms as 16 interleaved 2^16-point tile transforms + one radix-16 pass
   int ntt3_t1 = 0;          // RONK_NTT3_T1: pass-1 twiddles ω_n^(k1·m) from a 128 MiB table instead of stepping
   int ntt3_pdl = 1;         // RONK_NTT3_PDL: programmatic dependent launch between the three passes
   int ntt3 = 1;             // RONK_NTT3: 2^24-point transforms as three passes of 256-point tiles (ntt3_kernel.cuh)
@@ -85,6 +89,7 @@ struct ronk_ctx {
   size_t slot_bytes[kSlots] = {};
   cudaEvent_t ev_h2d[kSlots] = {}, ev_compute[kSlots] = {}, ev_d2h[kSlots] = {};
   bool slot_pending[kSlots] = {};
+  int cluster16_state = 0;   // ntt16c_kernel: 0 = not probed, 1 = usable, -1 = the device refuses 16-CTA clusters of its footprint
   void* dist = nullptr;      // ronk::DistState (dist.cu): communicator, peer mappings, staging — null until ronk_dist_init
   void* msm_ytab = nullptr;  // uint16_t[20402]: y of the curve point in each histogram bin (msm.cu), built on first use
   void* msm_done = nullptr;  // u32 completion counter of msm_hist_finish_kernel

@@ -197,16 +197,22 @@ int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 l
   return 0;
 }
 
+int g_ntt3_ng1 = 0;  // 1: the 256-thread (one group per thread) flavour of the 2^16 / 2^20 tile passes
 // The three-pass 2^24 transform (ntt3_kernel.cuh), phase by phase like ntt3_kernel; tables as run_ntt3() builds them.
 template <class F, int PASS, bool INV, int LOGN, bool BOUNDED = false>
 void run_pass3(const F& f, const Ntt3Args& A) {
   std::vector<u64> smem(N3_TILE_WORDS);
-  for (u32 tile = 0; tile < A.batch * (LOGN == 24 ? 4096u : 16u); tile++) {
+  for (u32 tile = 0; tile < A.batch * (LOGN == 24 ? 4096u : LOGN == 20 ? 256u : 16u); tile++) {
     u64 in_base, in_row, in_col, out_base, out_row;
     u32 m_base;
     n3_tile_geometry<PASS, LOGN>(tile, &in_base, &in_row, &in_col, &out_base, &out_row, &m_base);
+    if (g_ntt3_ng1 && LOGN != 24) {   // one group per thread, 256 threads per tile (grids that do not fill the GPU)
+      for (u32 t = 0; t < 2 * N3_THREADS; t++) n3_round0<F, PASS, INV, false, 1>(f, smem.data(), A, in_base, in_row, in_col, t);
+      for (u32 t = 0; t < 2 * N3_THREADS; t++) n3_round1<F, PASS, INV, false, LOGN, 1>(f, smem.data(), A, out_base, out_row, m_base, t);
+      continue;
+    }
     for (u32 t = 0; t < N3_THREADS; t++) n3_round0<F, PASS, INV, BOUNDED && PASS == (LOGN == 24 ? 1 : 2)>(f, smem.data(), A, in_base, in_row, in_col, t);
-    for (u32 t = 0; t < N3_THREADS; t++) n3_round1<F, PASS, INV, BOUNDED>(f, smem.data(), A, out_base, out_row, m_base, t);
+    for (u32 t = 0; t < N3_THREADS; t++) n3_round1<F, PASS, INV, BOUNDED, LOGN>(f, smem.data(), A, out_base, out_row, m_base, t);
   }
 }
 int g_ntt3_t1 = 0;  // 1: pass-1 twiddles from the n-word table
@@ -231,6 +237,10 @@ int run3(const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 batch, const u
       }
     }
   }
+  if (LOGN == 20) {                                      // the plan's 10 / 10 split of the two-level tables
+    tw_lo = table(f, wf, 1, 1024);
+    tw_hi = table(f, h_powmod(wf, 1024, p), 1, 1024);
+  }
   const u64 ninv = INV ? h_powmod(n % p, p - 2, p) : 1;
   std::vector<u64> t2(65536);
   const u64 w16 = h_powmod(w, n >> 16, p);
@@ -241,6 +251,16 @@ int run3(const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 batch, const u
   A.t1 = t1.empty() ? nullptr : t1.data();
   A.src_len = src_len; A.dst_len = dst_len;
   A.src = src ? src : data; A.dst = ws.data();          // the flow of run_ntt3(): src → ws, ws in place, ws → data
+  if constexpr (LOGN == 20) {                            // A1 src → data, A2 data → ws, C ws → data
+    A.dst = data;
+    run_pass3<F, 2, INV, 20>(f, A);
+    A.src = data; A.dst = ws.data();
+    run_pass3<F, 1, INV, 20>(f, A);
+    A.src = ws.data(); A.dst = data; A.mul_src = mul; A.flags = mul ? NTT_FLAG_MUL : 0;
+    for (u64 b = 0; b < batch; b++)
+      for (u64 k2 = 0; k2 < 65536; k2++) n3c_point<F, INV>(f, A, b, k2);
+    return 0;
+  }
   if (LOGN == 24) {
     run_pass3<F, 1, INV, LOGN, BOUNDED>(f, A);
     A.src = ws.data();
@@ -248,6 +268,47 @@ int run3(const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 batch, const u
   run_pass3<F, 2, INV, LOGN, BOUNDED && LOGN == 16>(f, A);
   A.src = ws.data(); A.dst = data; A.mul_src = mul; A.flags = mul ? NTT_FLAG_MUL : 0;
   run_pass3<F, 3, INV, LOGN, BOUNDED>(f, A);
+  return 0;
+}
+
+// ntt16c_kernel on the host: the sixteen CTAs of a cluster one after the other, phase by phase (both cluster barriers
+// become the boundary between the loops); each CTA's receive buffer is a host array the others write through `remote`.
+struct HostRemote {
+  u64* const* bufs;
+  u64* operator()(u32 rank) const { return bufs[rank]; }
+};
+template <class F, bool INV>
+int run16_cluster(const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 batch) {
+  const u64 n = 65536;
+  u64 w = h_powmod(g, (p - 1) / n, p);
+  if (INV) w = h_powmod(w, p - 2, p);
+  auto tw256 = table(f, h_powmod(w, n >> 8, p), 1, 256);
+  const u64 ninv = INV ? h_powmod(n % p, p - 2, p) : 1;
+  std::vector<u64> t2(65536);
+  for (u32 i = 0; i < 65536; i++) t2[i] = f.to_tw(f.mul(field_pow(f, w, (u64)((i >> 8) * (i & 255u))), ninv));
+  Ntt3Args A = {};
+  A.tw256 = tw256.data(); A.t2 = t2.data(); A.batch = batch; A.src_len = A.dst_len = ~0ULL;
+  A.src = data; A.dst = data; A.mul_src = mul; A.flags = mul ? NTT_FLAG_MUL : 0;
+  for (u32 b = 0; b < batch; b++) {
+    std::vector<std::vector<u64>> tile(16, std::vector<u64>(N3_TILE_WORDS)), recv(16, std::vector<u64>(N3_RECV_WORDS));
+    u64* bufs[16];
+    for (int r = 0; r < 16; r++) bufs[r] = recv[r].data();
+    u64 in_base, in_row, in_col, out_base, out_row;
+    u32 m_base;
+    for (u32 r = 0; r < 16; r++) {  // up to the first cluster barrier: every input of the transform is in shared memory
+      n3_tile_geometry<2, 16>(16 * b + r, &in_base, &in_row, &in_col, &out_base, &out_row, &m_base);
+      for (u32 t = 0; t < 2 * N3_THREADS; t++) n3_round0<F, 2, INV, false, 1>(f, tile[r].data(), A, in_base, in_row, in_col, t);
+    }
+    for (u32 r = 0; r < 16; r++)    // between the barriers: remote stores
+      for (u32 t = 0; t < 2 * N3_THREADS; t++) n3_round1_cluster<F, INV, 1>(f, tile[r].data(), A, r, t, HostRemote{bufs});
+    for (u32 r = 0; r < 16; r++) {  // after the second barrier: pass 3 out of the receive buffer, in place on the data
+      Ntt3Args B = A;
+      B.src = recv[r].data();
+      for (u32 t = 0; t < 2 * N3_THREADS; t++) n3_round0<F, 3, INV, false, 1>(f, tile[r].data(), B, 0, 1, N3_RECV_STRIDE, t);
+      n3_tile_geometry<3, 16>(16 * b + r, &in_base, &in_row, &in_col, &out_base, &out_row, &m_base);
+      for (u32 t = 0; t < 2 * N3_THREADS; t++) n3_round1<F, 3, INV, false, 16, 1>(f, tile[r].data(), A, out_base, out_row, m_base, t);
+    }
+  }
   return 0;
 }
 
@@ -319,12 +380,21 @@ int emu_ntt(uint64_t p, uint64_t g, uint64_t* data, const uint64_t* mul, uint32_
 // Goldilocks (g = 7) 2^24- or 2^16-point transforms through the 256-point-tile kernel functions.
 int emu_ntt3(uint64_t* data, const uint64_t* mul, uint32_t log_n, uint32_t batch, int inverse, int t1_table) {
   GoldilocksField f;
-  g_ntt3_t1 = t1_table;
+  g_ntt3_t1 = t1_table & 1;
+  g_ntt3_ng1 = (t1_table >> 1) & 1;   // bit 1 of the switch word: one group per thread
   if (log_n == 24)
     return inverse ? run3<GoldilocksField, true, 24>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 24>(f, GL_P, 7, data, mul, batch);
   if (log_n == 16)
     return inverse ? run3<GoldilocksField, true, 16>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 16>(f, GL_P, 7, data, mul, batch);
+  if (log_n == 20)
+    return inverse ? run3<GoldilocksField, true, 20>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 20>(f, GL_P, 7, data, mul, batch);
   return 1;
+}
+// a batch of 2^16-point transforms through the cluster formulation (ntt16c_kernel), in place
+int emu_ntt16_cluster(uint64_t* data, const uint64_t* mul, uint32_t batch, int inverse) {
+  GoldilocksField f;
+  return inverse ? run16_cluster<GoldilocksField, true>(f, GL_P, 7, data, mul, batch)
+                 : run16_cluster<GoldilocksField, false>(f, GL_P, 7, data, mul, batch);
 }
 // one bounded 2^24 transform, as the polynomial product uses it: dst[0, dst_len) = NTT(src[0, src_len) zero-extended) [⊙ mul]
 int emu_ntt3_bounded(const uint64_t* src, uint64_t src_len, uint64_t* dst, uint64_t dst_len, const uint64_t* mul, int inverse) {

@@ -324,3 +324,76 @@ def test_three_pass_batch_of_2_24():
     c.sync()
     assert torch.equal(both, a)
 
+
+
+def test_2_20_interleaved_tile_path():
+    """BASELINE config 2's size through the 256-point-tile kernels (16 interleaved 2^16-point transforms + the radix-16
+    pass): a batch of 3 bit-exact against the oracle, fused multiply, inverse round trip, out-of-place source — and
+    bit-for-bit agreement with the two-pass tile kernel (RONK_NTT3_20=0)."""
+    import os
+    import torch
+    from ronkathon_b200 import Context, ops
+    c0 = ctx()
+    n, batch = 1 << 20, 3
+    a = oracle.splitmix(GL, 77, n * batch)
+    m = oracle.splitmix(GL, 78, n * batch)
+    x = dev(a)
+    ops.ntt_(c0, x, 20, batch)
+    X = host(x)
+    for b in range(batch):
+        assert np.array_equal(X[b * n:(b + 1) * n], oracle.ntt_fast(GL, a[b * n:(b + 1) * n])), b
+    y = dev(a)
+    ops.ntt_mul_(c0, y, dev(m), 20, batch)
+    assert np.array_equal(host(y), oracle.vec_mul(GL, X, m))
+    ops.ntt_(c0, x, 20, batch, inverse=True)
+    assert np.array_equal(host(x), a)
+    os.environ["RONK_NTT3_20"] = "0"
+    try:
+        c1 = Context(0, torch.cuda.current_stream().cuda_stream)
+    finally:
+        os.environ.pop("RONK_NTT3_20")
+    z = dev(a)
+    ops.ntt_(c1, z, 20, batch)
+    c1.sync()
+    assert np.array_equal(host(z), X)
+    c1.close()
+
+
+def test_2_16_cluster_kernel_matches_the_two_launch_path():
+    """Small batches of 2^16-point transforms take ntt16c_kernel (one launch, a 16-CTA cluster per transform, the
+    pass-2 → pass-3 exchange through distributed shared memory, in place).  Forward against the oracle, fused
+    multiply, inverse round trip, for every batch size up to the switch-over and one beyond it, and bit-for-bit
+    agreement with a context that never uses the cluster kernel."""
+    import os
+    import torch
+    from ronkathon_b200 import Context, ops
+    c0 = ctx()
+    os.environ["RONK_NTT16_CLUSTER_MAX_BATCH"] = "0"
+    try:
+        c1 = Context(0, torch.cuda.current_stream().cuda_stream)
+    finally:
+        os.environ.pop("RONK_NTT16_CLUSTER_MAX_BATCH")
+    n = 1 << 16
+    for batch in (1, 2, 3, 8, 9):
+        a = oracle.splitmix(GL, 300 + batch, n * batch)
+        m = oracle.splitmix(GL, 400 + batch, n * batch)
+        x = dev(a)
+        ops.ntt_(c0, x, 16, batch)
+        X = host(x)
+        for b in (0, batch - 1):
+            assert np.array_equal(X[b * n:(b + 1) * n], oracle.ntt_fast(GL, a[b * n:(b + 1) * n])), (batch, b)
+        z = dev(a)
+        ops.ntt_(c1, z, 16, batch)
+        c1.sync()
+        assert np.array_equal(host(z), X), batch
+        y = dev(a)
+        ops.ntt_mul_(c0, y, dev(m), 16, batch)
+        assert np.array_equal(host(y), oracle.vec_mul(GL, X, m)), batch
+        ops.ntt_(c0, x, 16, batch, inverse=True)
+        assert np.array_equal(host(x), a), batch
+    # the launch counter shows which path ran: one launch per call through the cluster kernel
+    x = dev(oracle.splitmix(GL, 5, n))
+    before = c0.launches
+    ops.ntt_(c0, x, 16, 1)
+    assert c0.launches - before == 1
+    c1.close()

@@ -37,6 +37,7 @@ def emu():
     lib.emu_fast12_tiles.restype = C.c_uint64
     lib.emu_ntt3.argtypes = [P64, P64, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
     lib.emu_ntt3_bounded.argtypes = [P64, C.c_uint64, P64, C.c_uint64, P64, C.c_int]
+    lib.emu_ntt16_cluster.argtypes = [P64, P64, C.c_uint32, C.c_int]
     return lib
 
 
@@ -300,6 +301,54 @@ def test_two_pass_256_tiles_2_16_batch(emu):
     assert emu.emu_ntt3(_ptr(Y), _ptr(m), 16, batch, 0, 0) == 0
     assert np.array_equal(Y, oracle.vec_mul(GL, X, m))
     assert emu.emu_ntt3(_ptr(X), None, 16, batch, 1, 0) == 0
+    assert np.array_equal(X, a)
+
+
+@pytest.mark.parametrize("log_n", [16, 20])
+def test_one_group_per_thread_flavour_of_the_tile_passes(emu, log_n):
+    """Grids that do not fill the GPU run the same tile functions with 256 threads and one radix-16 group each
+    (switch bit 1 of the emulator): forward against the oracle, inverse round trip."""
+    n = 1 << log_n
+    a = oracle.splitmix(GL, 31 + log_n, n)
+    X = a.copy()
+    assert emu.emu_ntt3(_ptr(X), None, log_n, 1, 0, 2) == 0
+    assert np.array_equal(X, oracle.ntt_fast(GL, a))
+    assert emu.emu_ntt3(_ptr(X), None, log_n, 1, 1, 2) == 0
+    assert np.array_equal(X, a)
+
+
+def test_2_16_cluster_formulation_in_place(emu):
+    """ntt16c_kernel's data flow on the host: pass 2 of the sixteen tiles writes into the receive buffers of the
+    sixteen pass-3 CTAs (distributed shared memory on the GPU), pass 3 runs out of them, in place on the operand —
+    a batch of 3 against the oracle, fused multiply, inverse."""
+    n, batch = 1 << 16, 3
+    a = oracle.splitmix(GL, 51, n * batch)
+    m = oracle.splitmix(GL, 52, n * batch)
+    X = a.copy()
+    assert emu.emu_ntt16_cluster(_ptr(X), None, batch, 0) == 0
+    for b in range(batch):
+        assert np.array_equal(X[b * n:(b + 1) * n], oracle.ntt_fast(GL, a[b * n:(b + 1) * n])), b
+    Y = a.copy()
+    assert emu.emu_ntt16_cluster(_ptr(Y), _ptr(m), batch, 0) == 0
+    assert np.array_equal(Y, oracle.vec_mul(GL, X, m))
+    assert emu.emu_ntt16_cluster(_ptr(X), None, batch, 1) == 0
+    assert np.array_equal(X, a)
+
+
+def test_2_20_as_sixteen_interleaved_2_16_transforms_plus_radix16(emu):
+    """2^20 (BASELINE config 2) = passes A1 / A2 of the tile kernel on 16 interleaved 2^16-point transforms + the
+    register-only radix-16 pass C: a batch of 2 against the oracle per transform, fused multiply, inverse."""
+    n, batch = 1 << 20, 2
+    a = oracle.splitmix(GL, 19, n * batch)
+    m = oracle.splitmix(GL, 20, n * batch)
+    X = a.copy()
+    assert emu.emu_ntt3(_ptr(X), None, 20, batch, 0, 0) == 0
+    for b in range(batch):
+        assert np.array_equal(X[b * n:(b + 1) * n], oracle.ntt_fast(GL, a[b * n:(b + 1) * n])), b
+    Y = a.copy()
+    assert emu.emu_ntt3(_ptr(Y), _ptr(m), 20, batch, 0, 0) == 0
+    assert np.array_equal(Y, oracle.vec_mul(GL, X, m))
+    assert emu.emu_ntt3(_ptr(X), None, 20, batch, 1, 0) == 0
     assert np.array_equal(X, a)
 
 

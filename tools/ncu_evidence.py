@@ -32,6 +32,16 @@ if which in ("all", "ntt16"):
     for _ in range(reps):
         ops.ntt_(ctx, b, 16, 512)
         ops.ntt_(ctx, b, 16, 512, inverse=True)
+if which in ("all", "ntt20"):   # BASELINE config 2: passes A1 / A2 of the tile kernel + the radix-16 pass C
+    c2 = ops.splitmix_fill(ctx, 1 << 20, 6, GL, "cuda")
+    for _ in range(reps):
+        ops.ntt_(ctx, c2, 20)
+        ops.ntt_(ctx, c2, 20, inverse=True)
+if which in ("all", "ntt16c"):  # one 2^16-point transform: the 16-CTA cluster kernel
+    c3 = ops.splitmix_fill(ctx, 1 << 16, 7, GL, "cuda")
+    for _ in range(reps):
+        ops.ntt_(ctx, c3, 16)
+        ops.ntt_(ctx, c3, 16, inverse=True)
 if which in ("all", "field"):
     x = ops.splitmix_fill(ctx, 1 << 24, 4, GL, "cuda")
     y = ops.splitmix_fill(ctx, 1 << 24, 5, GL, "cuda")
