@@ -99,6 +99,7 @@ extern "C" {
   pub fn ronk_dist_shard_range(total: u64, rank: c_int, world: c_int, lo: *mut u64, hi: *mut u64) -> c_int;
   pub fn ronk_ntt_u64_batch_sharded(ctx: *mut ronk_ctx, p: u64, g: u64, shard: *mut u64, log_n: u32, total_batch: u64, inverse: c_int, lo: *mut u64, hi: *mut u64) -> c_int;
   pub fn ronk_ntt_u64_dist(ctx: *mut ronk_ctx, p: u64, g: u64, local: *mut u64, log_n: u32, batch: u32, flavour: c_int) -> c_int;
+  pub fn ronk_ntt_u64_dist_virtual(ctx: *mut ronk_ctx, p: u64, g: u64, data: *mut u64, log_n: u32, batch: u32, log_g: u32, flavour: c_int) -> c_int;
   pub fn ronk_msm_pluto_ext_dist(ctx: *mut ronk_ctx, points: *const u8, n_points: usize, scalars: *const u8, n_scalars: usize, out: *mut u8) -> c_int;
 }
 

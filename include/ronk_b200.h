@@ -166,6 +166,11 @@ int ronk_ntt_u64_batch_sharded(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *
  * ranks: `local` holds [batch][n/G] with local[b][j] = a_b[rank + G·j].  In place; on return
  * local[b][q][k] = X_b[rank·(n/G²) + k + (n/G)·q], q < G, k < n/G² (block-cyclic).  Collective. */
 int ronk_ntt_u64_dist(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *local, uint32_t log_n, uint32_t batch, int flavour);
+/* The same decomposition with G = 2^log_g (2 … 16) VIRTUAL ranks on ONE device, no communicator: `data` holds the G
+ * local slices rank-major ([rank][batch][n/G], slice r = a_b[r + G·j]) and receives the G local results in the
+ * layout above.  Every kernel of the chosen flavour runs as in the collective call; only the wire (all-to-all / peer
+ * buffers) is device-local.  Validation of G = 4, 8, 16 on a single GPU; not collective. */
+int ronk_ntt_u64_dist_virtual(ronk_ctx *ctx, uint64_t p, uint64_t g, uint64_t *data, uint32_t log_n, uint32_t batch, uint32_t log_g, int flavour);
 /* kzg::commit over index-range shards: this rank's terms in, the full commitment out on every rank
  * (RONK_EINVAL on every rank if any shard holds an invalid term).  Collective, synchronous. */
 int ronk_msm_pluto_ext_dist(ronk_ctx *ctx, const uint8_t *points, size_t n_points, const uint8_t *scalars, size_t n_scalars, uint8_t out[4]);

@@ -348,6 +348,11 @@ inline void ntt(Context& c, uint64_t p, uint64_t g, uint64_t* local, uint32_t lo
                 int flavour = RONK_DIST_FUSED) {
   c.check(ronk_ntt_u64_dist(c.get(), p, g, local, log_n, batch, flavour));
 }
+// G = 2^log_g virtual ranks on one device (validation / capacity mode): data = [rank][batch][n/G]
+inline void ntt_virtual(Context& c, uint64_t p, uint64_t g, uint64_t* data, uint32_t log_n, uint32_t batch, uint32_t log_g,
+                        int flavour = RONK_DIST_FUSED) {
+  c.check(ronk_ntt_u64_dist_virtual(c.get(), p, g, data, log_n, batch, log_g, flavour));
+}
 inline AffinePoint commit(Context& c, const uint8_t* points, const uint8_t* scalars, size_t n) {
   AffinePoint out;
   c.check(ronk_msm_pluto_ext_dist(c.get(), points, n, scalars, n, out.raw.data()));

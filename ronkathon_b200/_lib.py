@@ -84,6 +84,7 @@ SIGNATURES = {
     "ronk_dist_shard_range": (i32, [u64, i32, i32, p64, p64]),
     "ronk_ntt_u64_batch_sharded": (i32, [vp, u64, u64, vp, u32, u64, i32, p64, p64]),
     "ronk_ntt_u64_dist": (i32, [vp, u64, u64, vp, u32, u32, i32]),
+    "ronk_ntt_u64_dist_virtual": (i32, [vp, u64, u64, vp, u32, u32, u32, i32]),
     "ronk_msm_pluto_ext_dist": (i32, [vp, vp, sz, vp, sz, vp]),
 }
 

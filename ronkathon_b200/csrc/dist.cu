@@ -481,6 +481,82 @@ int ronk_ntt_u64_dist(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* local, ui
   return cross_rank(ctx, p, g, lg, src, (u64*)local, blk, batch, blk, 0, m);
 }
 
+// The same decomposition with G = 2^log_g VIRTUAL ranks on ONE device — no communicator, no IPC: `data` holds the G local
+// slices rank-major ([rank][batch][n/G], slice r = a[r::G] of every transform) and receives the G local results in the
+// layout ronk_ntt_u64_dist leaves on rank r ([batch][G][n/G²]).  Every kernel and every index formula of both
+// exchange flavours runs exactly as in the multi-GPU call (local transforms with the twiddle column in the store phase,
+// pack, cross_rank_kernel<log_g>); only the wire is replaced — device-to-device copies for the all-to-all, plain device
+// pointers for the peer buffers.  It exists so that G = 4, 8, 16 can be validated on a single GPU
+// (tests/test_gpu_ntt.py::test_virtual_rank_distributed_transform) and as a capacity mode for one device.
+int ronk_ntt_u64_dist_virtual(ronk_ctx* ctx, uint64_t p, uint64_t g, uint64_t* data, uint32_t log_n, uint32_t batch,
+                              uint32_t log_g, int flavour) {
+  ronk::DeviceGuard _dg(ctx);
+  if (!ctx || !data) return set_err(ctx, RONK_EINVAL, "null argument");
+  RONK_TRY(validate_modulus(ctx, p));
+  if (g == 0 || g >= p) return set_err(ctx, RONK_EINVAL, "generator out of range");
+  if (log_n >= 64 || (p - 1) % ((u64)1 << log_n) != 0)
+    return set_err(ctx, RONK_EINVAL, "n must divide p - 1 (no primitive n-th root of unity)");
+  if (log_g < 1 || log_g > 4) return set_err(ctx, RONK_EINVAL, "2 <= G <= 16");
+  if (log_n < 2 * log_g) return set_err(ctx, RONK_EINVAL, "transform smaller than G² points");
+  if (log_n - log_g > 26) return set_err(ctx, RONK_EUNSUPPORTED, "local transform larger than 2^26");
+  if (flavour != RONK_DIST_NCCL && flavour != RONK_DIST_FUSED) return set_err(ctx, RONK_EINVAL, "unknown flavour");
+  if (batch == 0) return RONK_OK;
+  const u32 log_m = log_n - log_g;
+  const int G = 1 << log_g;
+  const size_t m = (size_t)1 << log_m, blk = m >> log_g, words = (size_t)batch * m, chunk = (size_t)batch * blk;
+  struct Scratch {
+    u64 *z = nullptr, *tw = nullptr, *pack = nullptr;
+    ~Scratch() { if (z) cudaFree(z); if (tw) cudaFree(tw); if (pack) cudaFree(pack); }
+  } sc;
+  RONK_CUDA(ctx, cudaMalloc((void**)&sc.z, (size_t)G * words * sizeof(u64)));   // FUSED: the G exchange buffers; NCCL: the G receive buffers
+  RONK_CUDA(ctx, cudaMalloc((void**)&sc.tw, m * sizeof(u64)));
+  if (flavour == RONK_DIST_NCCL) RONK_CUDA(ctx, cudaMalloc((void**)&sc.pack, words * sizeof(u64)));
+  const u64 w = h_powmod(g, (p - 1) >> log_n, p);
+  for (int r = 0; r < G; r++) {   // Z_r = NTT_m(a[r::G]) ⊙ ω_n^(r·k')
+    u64* local = (u64*)data + (size_t)r * words;
+    const u64* twcol = nullptr;
+    if (r) {
+      RONK_TRY(ronk_field_powers_u64(ctx, p, h_powmod(w, (u64)r, p), 1 % p, (uint64_t*)sc.tw, m));
+      twcol = sc.tw;
+    }
+    if (flavour == RONK_DIST_FUSED) {
+      RONK_TRY(ntt_device_shared_mul(ctx, p, g, local, sc.z + (size_t)r * words, twcol, log_m, batch));
+    } else {
+      RONK_TRY(ntt_device_shared_mul(ctx, p, g, local, local, twcol, log_m, batch));
+      const u64* sendbase = local;
+      if (batch > 1) {
+        size_t blocks = (words + 255) / 256;
+        const size_t cap = (size_t)ctx->sm_count * 16;
+        if (blocks > cap) blocks = cap;
+        {
+          LaunchScope ls(ctx, "dist_pack");
+          pack_blocks_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(local, sc.pack, blk, log_g, batch);
+        }
+        RONK_TRY(check_launch(ctx, "pack_blocks_kernel"));
+        sendbase = sc.pack;
+      }
+      // the all-to-all: source r's chunk for destination s lands in s's receive buffer at slot r
+      for (int s2 = 0; s2 < G; s2++)
+        RONK_CUDA(ctx, cudaMemcpyAsync(sc.z + (size_t)s2 * words + (size_t)r * chunk, sendbase + (size_t)s2 * chunk,
+                                       chunk * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  for (int r = 0; r < G; r++) {   // rank r's cross-rank stage
+    PeerPtrs src;
+    for (int q = 0; q < 16; q++) src.p[q] = nullptr;
+    u64* local = (u64*)data + (size_t)r * words;
+    if (flavour == RONK_DIST_FUSED) {
+      for (int q = 0; q < G; q++) src.p[q] = sc.z + (size_t)q * words;
+      RONK_TRY(cross_rank(ctx, p, g, log_g, src, local, blk, batch, m, (size_t)r * blk, m));
+    } else {
+      for (int q = 0; q < G; q++) src.p[q] = sc.z + (size_t)r * words + (size_t)q * chunk;
+      RONK_TRY(cross_rank(ctx, p, g, log_g, src, local, blk, batch, blk, 0, m));
+    }
+  }
+  RONK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the scratch buffers are freed on return
+  return RONK_OK;
+}
+
 int ronk_msm_pluto_ext_dist(ronk_ctx* ctx, const uint8_t* points, size_t n_points, const uint8_t* scalars,
                             size_t n_scalars, uint8_t out[4]) {
   ronk::DeviceGuard _dg(ctx);

@@ -48,7 +48,10 @@ constexpr u64 GL_EPS = 0xFFFFFFFFULL;  // 2^64 mod p
 // add-family form is the faster one where ptxas keeps it on the FMA pipe.  RONK_FMA_TAIL selects it
 // per operation: bit 0 sub, bit 1 add, bit 2 both reduce tails, bit 3 / bit 4 first / second reduce
 // tail only.  Measured on B200 (2^24 transform): 0 → 0.437 ms, 1 → 0.421, 2 → 0.424, 3 → 0.411,
-// 4 → 0.427, 7 → 0.418, 11 / 19 → 0.411; 3 is the default.
+// 4 → 0.427, 7 → 0.418, 11 / 19 → 0.411 on the round-1 kernel; 3 is the default.  On the 256-point-tile kernel (round 2,
+// profiles/r02m_ab.txt, 5 CTAs per SM): 3 → 0.2564 ms, 11 → 0.2566, 19 → 0.2552, 0 → 0.295 (at 6 CTAs) — but the longer
+// add-family chains of 19 cost a single 2^20-point transform 2 µs (0.0351 vs 0.0331 ms: latency-bound, few warps), so
+// 3 stays.
 #ifndef RONK_FMA_TAIL
 #define RONK_FMA_TAIL 3
 #endif

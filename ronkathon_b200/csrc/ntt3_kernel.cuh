@@ -56,8 +56,18 @@ namespace ronk {
 #ifndef RONK_NTT3_UNROLL_GROUPS
 #define RONK_NTT3_UNROLL_GROUPS 1
 #endif
+#ifndef RONK_NTT3_STEP2
+// 1: the stepped twiddle (pass 1 of 2^24, pass A2 of 2^20) as two interleaved chains.  Measured (profiles/r02o_ab.txt):
+// neutral at 2^24 (0.2563 / 0.2572 vs 0.2562 / 0.2564 ms), −12 % on ONE 2^20-point transform (0.0291 vs 0.0329 ms:
+// few warps, the dependent chain is exposed) — on.
+#define RONK_NTT3_STEP2 1
+#endif
 #ifndef RONK_NTT3_MINB
-#define RONK_NTT3_MINB 6   // CTAs per SM the register budget is set for (6 × 35 KB is also the shared-memory limit)
+// CTAs per SM the register budget is set for.  6 (80 registers; 6 × 35 KB is also the shared-memory limit) was the first
+// choice; measured on B200 (profiles/r02m_ab.txt): 5 (102 registers, no spills in pass 3) 0.2564 ms vs 0.2650 ms per
+// 2^24 transform, 4 (128 registers) 0.2621 — the ALU pipe is the limiter and 20 warps with more registers feed it
+// better than 24 with fewer.
+#define RONK_NTT3_MINB 5
 #endif
 constexpr u32 N3_THREADS = 128;   // NG = 2 groups per thread (full grids); NG = 1: 256 threads, one group each — twice
                                   // the warps per tile for grids that do not fill the GPU (single 2^16 / 2^20 transforms)
@@ -151,11 +161,23 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
       if (INV) { ex0 = (0u - ex0) & EMASK; exd = (0u - exd) & EMASK; }
       u64 w = f.mul_tw(ld_tw(A.tw_lo + (ex0 & ((1u << LO) - 1u))), ld_tw(A.tw_hi + (ex0 >> LO)));
       const u64 rho = f.mul_tw(ld_tw(A.tw_lo + (exd & ((1u << LO) - 1u))), ld_tw(A.tw_hi + (exd >> LO)));
+#if RONK_NTT3_STEP2
+      // two interleaved stepping chains (even / odd rows, ratio ρ²): one more multiply per group, half the dependent chain
+      const u64 rho2 = f.mul_tw(rho, rho);
+      u64 w1 = f.mul_tw(w, rho);
+#pragma unroll
+      for (int qp = 0; qp < 16; qp += 2) {
+        o[(u64)qp * 16u * row_stride] = f.mul_tw(x[n3_br4(qp)], w);
+        o[(u64)(qp + 1) * 16u * row_stride] = f.mul_tw(x[n3_br4(qp + 1)], w1);
+        if (qp < 14) { w = f.mul_tw(w, rho2); w1 = f.mul_tw(w1, rho2); }
+      }
+#else
 #pragma unroll
       for (int qp = 0; qp < 16; qp++) {
         o[(u64)qp * 16u * row_stride] = f.mul_tw(x[n3_br4(qp)], w);
         if (qp < 15) w = f.mul_tw(w, rho);
       }
+#endif
     } else if (PASS == 2) {
       // ω_65536^(±k2·j3) from the 64 Ki-entry table [k2][j3]; m_base = first j3 of the tile
       // 2^20 (pass A1): ω_65536^(k2l·j2l) with j2l = m_base the same for all sixteen columns

@@ -47,8 +47,10 @@ struct NttPlan {
 // Tuning switches, read from the environment ONCE at ronk_ctx_create (never on the launch path).
 struct ronk_tune {
   int ntt3_min_batch16 = 1; // RONK_NTT3_MIN_BATCH16: smallest batch of 2^16-point transforms that takes the 256-point-tile kernels
-  int ntt16_cluster_max_batch = 8;  // RONK_NTT16_CLUSTER_MAX_BATCH: up to this many 2^16-point transforms go through ntt16c_kernel
-                                    // (one launch, 16-CTA cluster per transform, DSMEM exchange); 0 = never
+  int ntt16_cluster_max_batch = 2;  // RONK_NTT16_CLUSTER_MAX_BATCH: up to this many 2^16-point transforms go through ntt16c_kernel
+                                    // (one launch, 16-CTA cluster per transform, DSMEM exchange, in place, no workspace); 0 = never.
+                                    // Measured (profiles/r02m_ab.txt): 10.5 µs per transform either way at batch 1–2, the two-launch
+                                    // path wins from batch 4 on (8 transforms: 10.9 vs 15.6 µs)
   int ntt3_ng1_tiles = 3;   // RONK_NTT3_NG1_TILES: grids below this many tiles per SM run one group per thread (256 threads per tile)
   int ntt3_20 = 1;          // RONK_NTT3_20: 2^20-point transforms as 16 interleaved 2^16-point tile transforms + one radix-16 pass
   int ntt3_t1 = 0;          // RONK_NTT3_T1: pass-1 twiddles ω_n^(k1·m) from a 128 MiB table instead of stepping

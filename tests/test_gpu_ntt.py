@@ -374,7 +374,13 @@ def test_2_16_cluster_kernel_matches_the_two_launch_path():
     finally:
         os.environ.pop("RONK_NTT16_CLUSTER_MAX_BATCH")
     n = 1 << 16
+    os.environ["RONK_NTT16_CLUSTER_MAX_BATCH"] = "8"   # the default switch-over is 2: widen it for this test
+    try:
+        c8 = Context(0, torch.cuda.current_stream().cuda_stream)
+    finally:
+        os.environ.pop("RONK_NTT16_CLUSTER_MAX_BATCH")
     for batch in (1, 2, 3, 8, 9):
+        c0 = c8
         a = oracle.splitmix(GL, 300 + batch, n * batch)
         m = oracle.splitmix(GL, 400 + batch, n * batch)
         x = dev(a)
@@ -392,8 +398,41 @@ def test_2_16_cluster_kernel_matches_the_two_launch_path():
         ops.ntt_(c0, x, 16, batch, inverse=True)
         assert np.array_equal(host(x), a), batch
     # the launch counter shows which path ran: one launch per call through the cluster kernel
+    c0 = ctx()                                          # the default context: one transform → one launch
     x = dev(oracle.splitmix(GL, 5, n))
+    ops.ntt_(c0, x, 16, 1)
     before = c0.launches
     ops.ntt_(c0, x, 16, 1)
     assert c0.launches - before == 1
     c1.close()
+    c8.close()
+
+
+@pytest.mark.parametrize("log_g", [1, 2, 3, 4])
+def test_virtual_rank_distributed_transform(log_g):
+    """ronk_ntt_u64_dist with G = 2, 4, 8, 16 VIRTUAL ranks on one device (ronk_ntt_u64_dist_virtual): the local
+    transforms with the twiddle column ω_n^(r·k') in their store phase, the pack kernel and cross_rank_kernel<log G> —
+    every kernel and index formula of both exchange flavours of the multi-GPU call — reassembled and compared with the
+    oracle bit for bit; Goldilocks and a generic (Montgomery) modulus, single transforms and batches."""
+    from ronkathon_b200 import _lib
+    from ronkathon_b200 import dist as rd
+    c = ctx()
+    G = 1 << log_g
+    cases = [(GL, 7, max(2 * log_g, 4), 1), (GL, 7, 12, 3), (GL, 7, 16 + log_g, 2), (GL, 7, 20, 1),
+             (2013265921, 31, 10, 2), (GL, pow(7, 5, GL), 12, 2)]
+    for p, g, log_n, batch in cases:
+        n, m = 1 << log_n, (1 << log_n) // G
+        blk = m // G
+        full = [oracle.splitmix(p, 600 + 7 * b + log_n, n) for b in range(batch)]
+        want = [oracle.ntt_fast(p, a, g=g) for a in full]
+        for flavour in (rd.DIST_NCCL, rd.DIST_FUSED):
+            loc = np.concatenate([np.concatenate([a[r::G] for a in full]) for r in range(G)])   # [rank][batch][m]
+            d = dev(loc)
+            c.call("ronk_ntt_u64_dist_virtual", p, g, _lib._ptr(d), log_n, batch, log_g, flavour)
+            out = host(d).reshape(G, batch, G, blk)                                             # [rank s][b][q][k]
+            for b in range(batch):
+                X = np.empty(n, dtype=np.uint64)
+                for s in range(G):
+                    for q in range(G):
+                        X[s * blk + m * q: s * blk + m * q + blk] = out[s, b, q]
+                assert np.array_equal(X, want[b]), (p, log_n, batch, flavour, b)

@@ -11,7 +11,8 @@ from ronkathon_b200 import ops, kzg, Polynomial, PlutoBaseField, PlutoScalarFiel
 
 c = ctx()
 ok = True
-for lg, batch in ((3, 5), (6, 3), (10, 2), (13, 1), (14, 1), (16, 1)):
+# (16, 1): the cluster kernel; (16, 3): the one-group-per-thread two-launch tile passes; (20, 1): passes A1 / A2 / C
+for lg, batch in ((3, 5), (6, 3), (10, 2), (13, 1), (14, 1), (16, 1), (16, 3), (20, 1)):
     a = oracle.splitmix(GL, lg, batch << lg)
     d = dev(a); ops.ntt_(c, d, lg, batch); X = host(d)
     ok &= all(np.array_equal(X[b << lg:(b + 1) << lg], oracle.ntt_fast(GL, a[b << lg:(b + 1) << lg])) for b in range(batch))
