@@ -196,6 +196,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     numa = bind_to_gpu_numa(local_rank)   # before torch creates its threads and before any pinned allocation
 
+    # This program's stdout is ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+    # version banner there when NCCL_DEBUG is set in the environment): everything before the JSON line goes to stderr.
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -393,6 +399,8 @@ def main():
             line["configs"] = configs
         if multi is not None:
             line["multi"] = multi
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
