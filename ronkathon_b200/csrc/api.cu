@@ -44,10 +44,10 @@ int ronk_ctx_create(ronk_ctx** out, int device, void* stream) {
   ctx->tune.pdl = env_int("RONK_PDL", 1);
   ctx->tune.ntt3 = env_int("RONK_NTT3", 1);
   ctx->tune.ntt3_pdl = env_int("RONK_NTT3_PDL", 1);
-  ctx->tune.ntt3_t1 = env_int("RONK_NTT3_T1", 0);
+  ctx->tune.ntt3_t1 = env_int("RONK_NTT3_T1", 1);
   ctx->tune.ntt3_20 = env_int("RONK_NTT3_20", 1);
   ctx->tune.ntt16_cluster_max_batch = env_int("RONK_NTT16_CLUSTER_MAX_BATCH", 2);
-  ctx->tune.ntt3_ng1_tiles = env_int("RONK_NTT3_NG1_TILES", 3);
+  ctx->tune.ntt3_ng1_tiles = env_int("RONK_NTT3_NG1_TILES", 6);
   ctx->tune.ntt3_min_batch16 = env_int("RONK_NTT3_MIN_BATCH16", 1);
   ctx->tune.single_tile_log = env_int("RONK_SINGLE_TILE_LOG", 12);
   ctx->tune.tile1 = env_int("RONK_TILE1", 14);

@@ -56,6 +56,13 @@ namespace ronk {
 #ifndef RONK_NTT3_UNROLL_GROUPS
 #define RONK_NTT3_UNROLL_GROUPS 1
 #endif
+#ifndef RONK_NTT3_EARLY_TW
+// bit 0: prefetch (L1) the pass-1 table twiddles of a group before its shared-memory reads and network; bit 1: the second
+// group's data rows (L2) during the first group's round 0; bit 2: the pass-2 table rows.  Measured (profiles/r02t_ab.txt,
+// r02u_ab.txt, ms per 2^24 transform): 0 → 0.2490, 1 → 0.2433 (pass 1: 0.1006 → 0.0953; L2 instead of L1: the same),
+// 3 → 0.2438, 5 → 0.2435, 7 → 0.2444 (and a single 2^20-point transform 0.0332 instead of 0.0291 ms) — bit 0 only.
+#define RONK_NTT3_EARLY_TW 1
+#endif
 #ifndef RONK_NTT3_STEP2
 // 1: the stepped twiddle (pass 1 of 2^24, pass A2 of 2^20) as two interleaved chains.  Measured (profiles/r02o_ab.txt):
 // neutral at 2^24 (0.2563 / 0.2572 vs 0.2562 / 0.2564 ms), −12 % on ONE 2^20-point transform (0.0291 vs 0.0329 ms:
@@ -104,6 +111,15 @@ RONK_DEV void n3_round0(const F& f, u64* smem, const Ntt3Args& A, u64 tile_base,
     const u32 g = tid + (u32)h * N3_THREADS;
     const u32 d0 = (PASS == 3) ? (g & 15u) : (g >> 4), c = (PASS == 3) ? (g >> 4) : (g & 15u);
     const u64* p = A.src + tile_base + (u64)d0 * row_stride + (u64)c * col_stride;
+#if (RONK_NTT3_EARLY_TW & 2) && defined(__CUDA_ARCH__)
+    if (NG == 2 && h == 0 && !BOUNDED) {   // the second group's sixteen rows on their way (L2) while the first is computed
+      const u32 g1 = g + N3_THREADS;
+      const u32 e0 = (PASS == 3) ? (g1 & 15u) : (g1 >> 4), e1 = (PASS == 3) ? (g1 >> 4) : (g1 & 15u);
+      const u64* pn = A.src + tile_base + (u64)e0 * row_stride + (u64)e1 * col_stride;
+#pragma unroll
+      for (int q = 0; q < 16; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + (u64)q * 16u * row_stride) : "memory");
+    }
+#endif
     u64 x[16];
 #pragma unroll
     for (int q = 0; q < 16; q++) {
@@ -138,12 +154,32 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
   for (int h = 0; h < NG; h++) {
     const u32 g = tid + (u32)h * N3_THREADS;
     const u32 d1 = g >> 4, c = g & 15u;
+    const u32 b = bitrev(d1, 4);
     const u64* s = smem + n3_word(d1, 0, c);
+#if (RONK_NTT3_EARLY_TW & 1) && defined(__CUDA_ARCH__)
+    // The table twiddles of this group are PREFETCHED (L1) before the shared-memory reads and the network: loaded where
+    // they are used (the compiler keeps them behind the run-time `if (A.t1)`, and sinks even explicit early loads to save
+    // registers), their DRAM latency was the top stall of pass 1 (ncu r02s: long_scoreboard 1.8 per issued instruction).
+    if (PASS == 1 && LOGN == 24) {
+      // no branch on A.t1 here (the compiler would merge it with the one below and sink the prefetches into it): without
+      // a table the prefetches go to sixteen harmless valid addresses (stride 0 on the 256-entry ω_256 table)
+      const u64* t = A.t1 ? A.t1 + ((u64)b << 16) + m_base + c : A.tw256;
+      const u64 st = A.t1 ? ((u64)1 << 20) : 0;
+#pragma unroll
+      for (int qp = 0; qp < 16; qp++) asm volatile("prefetch.global.L1 [%0];" ::"l"(t + (u64)qp * st) : "memory");
+    }
+#endif
+#if (RONK_NTT3_EARLY_TW & 4) && defined(__CUDA_ARCH__)
+    if (PASS == 2) {   // the L2-resident 64 Ki-entry table of pass 2 (pass A1 of 2^20), same idea
+      const u64* t = A.t2 + ((u64)b << 8) + m_base + (LOGN == 20 ? 0u : c);
+#pragma unroll
+      for (int qp = 0; qp < 16; qp++) asm volatile("prefetch.global.L1 [%0];" ::"l"(t + ((u64)qp << 12)) : "memory");
+    }
+#endif
     u64 x[16];
 #pragma unroll
     for (int q = 0; q < 16; q++) x[q] = s[n3_word(0, (u32)q, 0)];
     radix_network<4, INV>(f, x);
-    const u32 b = bitrev(d1, 4);
     u64* o = A.dst + tile_base + (u64)b * row_stride + c;   // row k = 16 q' + b, q' = bitrev4(register index)
     if (PASS == 1 && LOGN == 24 && A.t1) {
       // ω_n^(±k1·m) from the n-word table [k1][m]: the same offsets as the stores, one coalesced load each

@@ -51,9 +51,12 @@ struct ronk_tune {
                                     // (one launch, 16-CTA cluster per transform, DSMEM exchange, in place, no workspace); 0 = never.
                                     // Measured (profiles/r02m_ab.txt): 10.5 µs per transform either way at batch 1–2, the two-launch
                                     // path wins from batch 4 on (8 transforms: 10.9 vs 15.6 µs)
-  int ntt3_ng1_tiles = 3;   // RONK_NTT3_NG1_TILES: grids below this many tiles per SM run one group per thread (256 threads per tile)
+  int ntt3_ng1_tiles = 6;   // RONK_NTT3_NG1_TILES: grids below this many tiles per SM run one group per thread (256 threads per tile);
+                            // measured (profiles/r02r_switches.txt): 6 vs 3 — two 2^20-point transforms 0.0453 vs 0.0488 ms, rest equal
   int ntt3_20 = 1;          // RONK_NTT3_20: 2^20-point transforms as 16 interleaved 2^16-point tile transforms + one radix-16 pass
-  int ntt3_t1 = 0;          // RONK_NTT3_T1: pass-1 twiddles ω_n^(k1·m) from a 128 MiB table instead of stepping
+  int ntt3_t1 = 1;          // RONK_NTT3_T1: pass-1 twiddles ω_n^(k1·m) of the 2^24-point transform from a 128 MiB table per direction
+                            // (built at first use; no memory → stepped) instead of stepping.  Measured: 1 % at 6 CTAs per SM (off
+                            // then), 3.4 % at 5 (0.2473 vs 0.2559 ms, profiles/r02r_switches.txt) — on
   int ntt3_pdl = 1;         // RONK_NTT3_PDL: programmatic dependent launch between the three passes
   int ntt3 = 1;             // RONK_NTT3: 2^24-point transforms as three passes of 256-point tiles (ntt3_kernel.cuh)
   int pdl = 1;              // RONK_PDL: programmatic dependent launch of pass 2 behind pass 1

@@ -283,7 +283,8 @@ def test_opt_in_kernel_variants_agree_with_the_default():
         c0.sync()
         assert torch.equal(z, a[: 1 << lg])
         ref[lg] = (x, y)
-    for env in ({"RONK_NTT3": "0"}, {"RONK_NTT3": "0", "RONK_FAST12": "1"}, {"RONK_NTT3": "0", "RONK_TW_TABLE": "1"}, {"RONK_PDL": "0"}):
+    for env in ({"RONK_NTT3": "0"}, {"RONK_NTT3": "0", "RONK_FAST12": "1"}, {"RONK_NTT3": "0", "RONK_TW_TABLE": "1"}, {"RONK_PDL": "0"},
+                {"RONK_NTT3_T1": "0"}, {"RONK_NTT3_PDL": "0"}):   # the stepped pass-1 twiddle (default: 128 MiB table), no PDL
         old = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
         try:
