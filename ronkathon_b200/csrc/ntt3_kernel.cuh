@@ -3,16 +3,16 @@
 // Same map as Polynomial::fft / ifft (src/polynomial/mod.rs:273-323, :430-484): X[k] = Σ_j a_j ω^(jk), natural order in
 // and out, canonical residues.  With j = j1·2^16 + j2·2^8 + j3 and k = k1 + k2·2^8 + k3·2^16 (all digits < 256):
 //
-//   pass 1  A1[k1, j2, j3] = ( Σ_j1 ω_256^(j1 k1) a[j1, j2, j3] ) · ω_n^(k1·(256 j2 + j3))        in place on the data
-//   pass 2  A2[k1, k2, j3] = ( Σ_j2 ω_256^(j2 k2) A1[k1, j2, j3] ) · ω_65536^(k2 j3)               data → workspace
+//   pass 1  A1[k1, j2, j3] = ( Σ_j1 ω_256^(j1 k1) a[j1, j2, j3] ) · ω_n^(k1·(256 j2 + j3))        src → workspace
+//   pass 2  A2[k1, k2, j3] = ( Σ_j2 ω_256^(j2 k2) A1[k1, j2, j3] ) · ω_65536^(k2 j3)               in place in the workspace
 //   pass 3  X[k1 + 256 k2 + 65536 k3] = Σ_j3 ω_256^(j3 k3) A2[k1, k2, j3]                          workspace → data
 //
 // Why three passes when two suffice (ntt_kernel.cuh): the two-pass kernel needs 64–128 KiB tiles, so an SM holds 16 warps
 // (4 per scheduler) and every tile goes through three CTA barriers and four shared-memory round trips; measured, it runs at
 // 68 % of its own integer-pipe floor and stripping a fifth of its instructions did not make it faster:
 // it is bound by latency hiding, not by instruction count.  A 256-point transform per tile needs 4096 elements (16 columns:
-// every global access is a full 128-byte line in all three passes) = 35 KB of shared memory and 128 threads: six CTAs per
-// SM (24 warps), ONE barrier and ONE shared-memory round trip per tile:
+// every global access is a full 128-byte line in all three passes) = 35 KB of shared memory and 128 threads: five CTAs per
+// SM (20 warps at 96 registers; six at 80 registers measured 3 % slower), ONE barrier and ONE shared-memory round trip per tile:
 //
 //   round 0   each thread loads its two radix-16 groups (digit d1 of the transform index) straight from HBM into
 //             registers, runs the shift-twiddle network, multiplies by ω_256^(d0·k_hi) and writes the tile;
@@ -21,8 +21,9 @@
 //             registers to the rows bitrev8 assigns them (no un-bit-reversing pass through shared memory).
 //
 // HBM traffic is 3 reads + 3 writes of the data (805 MB at 2^24) instead of 2 + 2: the kernel is integer-pipe-bound with
-// HBM at < 20 % of its peak, so the bytes are there to spend.  General multiplications per element: 3·15/16 (inner) + 2
-// (pass 1: stepped ω_n^(k1·m), apply) + 1 (pass 2: 64 Ki-entry table, L2-resident) = 5.8, as in the two-pass kernel.
+// HBM at < 20 % of its peak, so the bytes are there to spend.  General multiplications per element: 3·15/16 (inner) + 1
+// (pass 1: ω_n^(k1·m) from the plan's 128 MiB table, prefetched; 2 when it is stepped instead) + 1 (pass 2: 64 Ki-entry
+// table, L2-resident) = 4.8 (5.8 stepped, as in the two-pass kernel).
 //
 // n = 2^20 (BASELINE config 2) reuses the two tile passes on SIXTEEN INTERLEAVED 2^16-point transforms and adds one
 // register-only radix-16 pass.  With j = j1 + 16·(256 j2h + j2l) and k = 65536 k1 + k2l + 256 k2h:
