@@ -351,10 +351,12 @@ static int run_ntt3(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, c
   const int d = INV ? 1 : 0;
   const u64 n = (u64)1 << LOGN;
   RONK_TRY((ntt3_tables<F, INV>(ctx, f, pl, LOGN)));
-  if (LOGN == 24 && ctx->tune.ntt3_t1 && !pl.t1[d]) {  // optional 128 MiB table of the pass-1 twiddles (no memory: stay stepped)
+  if ((LOGN == 24 || LOGN == 20) && ctx->tune.ntt3_t1 && !pl.t1[d]) {  // n-word table of the stepped twiddles: 128 MiB (2^24) / 8 MiB (2^20) per direction; no memory: stay stepped
+    if (LOGN == 20 && (pl.log_n1 != 10 || !pl.tw_lo || !pl.tw2)) return set_err(ctx, RONK_ECUDA, "internal: unexpected 2^20 plan shape");
     if (cudaMalloc((void**)&pl.t1[d], n * sizeof(u64)) == cudaSuccess) {
       LaunchScope ls(ctx, "ntt3_t1");
-      ntt3_t1_kernel<F><<<(unsigned)(n / 256), 256, 0, ctx->stream>>>(f, pl.tw_lo, pl.tw2, INV ? 1 : 0, pl.t1[d]);
+      if (LOGN == 24) ntt3_t1_kernel<F><<<(unsigned)(n / 256), 256, 0, ctx->stream>>>(f, pl.tw_lo, pl.tw2, INV ? 1 : 0, pl.t1[d]);
+      else ntt3_t1_20_kernel<F><<<(unsigned)(n / 256), 256, 0, ctx->stream>>>(f, pl.tw_lo, pl.tw2, INV ? 1 : 0, pl.t1[d]);
     } else {
       cudaGetLastError();
       pl.t1[d] = nullptr;

@@ -161,11 +161,13 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
     // The table twiddles of this group are PREFETCHED (L1) before the shared-memory reads and the network: loaded where
     // they are used (the compiler keeps them behind the run-time `if (A.t1)`, and sinks even explicit early loads to save
     // registers), their DRAM latency was the top stall of pass 1 (ncu r02s: long_scoreboard 1.8 per issued instruction).
-    if (PASS == 1 && LOGN == 24) {
+    if (PASS == 1 && (LOGN == 24 || LOGN == 20)) {
       // no branch on A.t1 here (the compiler would merge it with the one below and sink the prefetches into it): without
-      // a table the prefetches go to sixteen harmless valid addresses (stride 0 on the 256-entry ω_256 table)
-      const u64* t = A.t1 ? A.t1 + ((u64)b << 16) + m_base + c : A.tw256;
-      const u64 st = A.t1 ? ((u64)1 << 20) : 0;
+      // a table the prefetches go to the sixteen lines this group is about to store to — valid, spread over the tile like
+      // the table rows (one shared address for all threads measured 2× slower: every warp of the GPU on one L1 line)
+      const u64* t = A.t1 ? (LOGN == 24 ? A.t1 + ((u64)b << 16) + m_base + c : A.t1 + 16u * m_base + ((u64)b << 12) + c)
+                          : A.dst + tile_base + (u64)b * row_stride + c;
+      const u64 st = A.t1 ? ((u64)1 << (LOGN == 24 ? 20 : 16)) : 16u * row_stride;
 #pragma unroll
       for (int qp = 0; qp < 16; qp++) asm volatile("prefetch.global.L1 [%0];" ::"l"(t + (u64)qp * st) : "memory");
     }
@@ -188,6 +190,14 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
       u64 w[16];
 #pragma unroll
       for (int qp = 0; qp < 16; qp++) w[qp] = ld_tw(t + ((u64)qp << 20));
+#pragma unroll
+      for (int qp = 0; qp < 16; qp++) o[(u64)qp * 16u * row_stride] = f.mul_tw(x[n3_br4(qp)], w[qp]);
+    } else if (PASS == 1 && LOGN == 20 && A.t1) {
+      // pass A2 of 2^20: ω_n^(±j1·k2) from the n-word table indexed like this pass's output (16·k2 + j1)
+      const u64* t = A.t1 + 16u * m_base + ((u64)b << 12) + c;
+      u64 w[16];
+#pragma unroll
+      for (int qp = 0; qp < 16; qp++) w[qp] = ld_tw(t + ((u64)qp << 16));
 #pragma unroll
       for (int qp = 0; qp < 16; qp++) o[(u64)qp * 16u * row_stride] = f.mul_tw(x[n3_br4(qp)], w[qp]);
     } else if (PASS == 1) {
@@ -429,6 +439,15 @@ __global__ void ntt3_t1_kernel(const F f, const u64* __restrict__ tw_lo, const u
   u32 ex = (k1 * m) & 0xFFFFFFu;
   if (inverse) ex = (0u - ex) & 0xFFFFFFu;
   out[i] = f.mul_tw(tw_lo[ex & 4095u], tw_hi[ex >> 12]);
+}
+
+// 2^20: T1[16·k2 + j1] = ω_n^(±j1·k2), k2 < 65536, j1 < 16 — indexed like the output of pass A2 (10 / 10 two-level tables)
+template <class F>
+__global__ void ntt3_t1_20_kernel(const F f, const u64* __restrict__ tw_lo, const u64* __restrict__ tw_hi, int inverse, u64* __restrict__ out) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;  // < 2^20
+  u32 ex = ((i >> 4) * (i & 15u)) & 0xFFFFFu;
+  if (inverse) ex = (0u - ex) & 0xFFFFFu;
+  out[i] = f.mul_tw(tw_lo[ex & 1023u], tw_hi[ex >> 10]);
 }
 
 // T2[k2][j3] = to_tw(ω_65536^(±k2·j3) · s): 64 Ki entries

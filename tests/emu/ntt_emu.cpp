@@ -240,6 +240,14 @@ int run3(const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 batch, const u
   if (LOGN == 20) {                                      // the plan's 10 / 10 split of the two-level tables
     tw_lo = table(f, wf, 1, 1024);
     tw_hi = table(f, h_powmod(wf, 1024, p), 1, 1024);
+    if (g_ntt3_t1) {                                     // mirrors ntt3_t1_20_kernel
+      t1.resize(n);
+      for (u64 i = 0; i < n; i++) {
+        u32 ex = (u32)((i >> 4) * (i & 15u)) & 0xFFFFFu;
+        if (INV) ex = (0u - ex) & 0xFFFFFu;
+        t1[i] = f.mul_tw(tw_lo[ex & 1023u], tw_hi[ex >> 10]);
+      }
+    }
   }
   const u64 ninv = INV ? h_powmod(n % p, p - 2, p) : 1;
   std::vector<u64> t2(65536);

@@ -348,16 +348,20 @@ def test_2_20_interleaved_tile_path():
     assert np.array_equal(host(y), oracle.vec_mul(GL, X, m))
     ops.ntt_(c0, x, 20, batch, inverse=True)
     assert np.array_equal(host(x), a)
-    os.environ["RONK_NTT3_20"] = "0"
-    try:
-        c1 = Context(0, torch.cuda.current_stream().cuda_stream)
-    finally:
-        os.environ.pop("RONK_NTT3_20")
-    z = dev(a)
-    ops.ntt_(c1, z, 20, batch)
-    c1.sync()
-    assert np.array_equal(host(z), X)
-    c1.close()
+    for env in ("RONK_NTT3_20", "RONK_NTT3_T1"):   # the two-pass tile kernel; the stepped pass-A2 twiddle (default: 8 MiB table)
+        os.environ[env] = "0"
+        try:
+            c1 = Context(0, torch.cuda.current_stream().cuda_stream)
+        finally:
+            os.environ.pop(env)
+        z = dev(a)
+        ops.ntt_(c1, z, 20, batch)
+        c1.sync()
+        assert np.array_equal(host(z), X), env
+        ops.ntt_(c1, z, 20, batch, inverse=True)
+        c1.sync()
+        assert np.array_equal(host(z), a), env
+        c1.close()
 
 
 def test_2_16_cluster_kernel_matches_the_two_launch_path():

@@ -335,20 +335,22 @@ def test_2_16_cluster_formulation_in_place(emu):
     assert np.array_equal(X, a)
 
 
-def test_2_20_as_sixteen_interleaved_2_16_transforms_plus_radix16(emu):
+@pytest.mark.parametrize("t1_table", [0, 1])
+def test_2_20_as_sixteen_interleaved_2_16_transforms_plus_radix16(emu, t1_table):
     """2^20 (BASELINE config 2) = passes A1 / A2 of the tile kernel on 16 interleaved 2^16-point transforms + the
-    register-only radix-16 pass C: a batch of 2 against the oracle per transform, fused multiply, inverse."""
+    register-only radix-16 pass C: a batch of 2 against the oracle per transform, fused multiply, inverse; pass A2's
+    twiddle stepped (0) or from the n-word table (1)."""
     n, batch = 1 << 20, 2
     a = oracle.splitmix(GL, 19, n * batch)
     m = oracle.splitmix(GL, 20, n * batch)
     X = a.copy()
-    assert emu.emu_ntt3(_ptr(X), None, 20, batch, 0, 0) == 0
+    assert emu.emu_ntt3(_ptr(X), None, 20, batch, 0, t1_table) == 0
     for b in range(batch):
         assert np.array_equal(X[b * n:(b + 1) * n], oracle.ntt_fast(GL, a[b * n:(b + 1) * n])), b
     Y = a.copy()
-    assert emu.emu_ntt3(_ptr(Y), _ptr(m), 20, batch, 0, 0) == 0
+    assert emu.emu_ntt3(_ptr(Y), _ptr(m), 20, batch, 0, t1_table) == 0
     assert np.array_equal(Y, oracle.vec_mul(GL, X, m))
-    assert emu.emu_ntt3(_ptr(X), None, 20, batch, 1, 0) == 0
+    assert emu.emu_ntt3(_ptr(X), None, 20, batch, 1, t1_table) == 0
     assert np.array_equal(X, a)
 
 
