@@ -62,6 +62,8 @@ namespace ronk {
 // group's data rows (L2) during the first group's round 0; bit 2: the pass-2 table rows.  Measured (profiles/r02t_ab.txt,
 // r02u_ab.txt, ms per 2^24 transform): 0 → 0.2490, 1 → 0.2433 (pass 1: 0.1006 → 0.0953; L2 instead of L1: the same),
 // 3 → 0.2438, 5 → 0.2435, 7 → 0.2444 (and a single 2^20-point transform 0.0332 instead of 0.0291 ms) — bit 0 only.
+// bit 3: the multiplier rows of the fused point-wise product in pass 3 (r02y_ab.txt): fused transform 0.2607 vs 0.2630 ms,
+// plain one 0.2427 vs 0.2404 — a wash, off.
 #define RONK_NTT3_EARLY_TW 1
 #endif
 #ifndef RONK_NTT3_STEP2
@@ -170,6 +172,14 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
       const u64 st = A.t1 ? ((u64)1 << (LOGN == 24 ? 20 : 16)) : 16u * row_stride;
 #pragma unroll
       for (int qp = 0; qp < 16; qp++) asm volatile("prefetch.global.L1 [%0];" ::"l"(t + (u64)qp * st) : "memory");
+    }
+#endif
+#if (RONK_NTT3_EARLY_TW & 8) && defined(__CUDA_ARCH__)
+    if (PASS == 3) {   // the point-wise multiplier rows of the fused product (poly_mul), same idea and same select trick
+      const bool fm = (A.flags & NTT_FLAG_MUL) != 0;
+      const u64* t = (fm ? A.mul_src : (const u64*)A.dst) + tile_base + (u64)b * row_stride + c;
+#pragma unroll
+      for (int qp = 0; qp < 16; qp++) asm volatile("prefetch.global.L1 [%0];" ::"l"(t + (u64)qp * 16u * row_stride) : "memory");
     }
 #endif
 #if (RONK_NTT3_EARLY_TW & 4) && defined(__CUDA_ARCH__)
