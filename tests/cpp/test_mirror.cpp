@@ -124,6 +124,24 @@ int main() {
     c.check(ronk_memcpy_h2d(c.get(), dp, pts.data(), pts.size()));
     c.check(ronk_memcpy_h2d(c.get(), ds, sc.data(), sc.size()));
     CHECK((dist::commit(c, (const uint8_t*)dp, (const uint8_t*)ds, sc.size()).raw == std::array<uint8_t, 4>{32, 0, 59, 0}));
+    // the distributed decomposition with G = 4 VIRTUAL ranks on this one device (both exchange flavours): slice r holds
+    // a[r::4]; rank s ends with [q][k] = X[s·blk + k + m·q] — reassembled, it must be the single-device transform
+    {
+      const uint32_t log_n = 10, log_g = 2, G = 4;
+      const size_t n = 1 << log_n, m = n / G, blk = m / G;
+      for (int flavour : {RONK_DIST_NCCL, RONK_DIST_FUSED}) {
+        std::vector<uint64_t> loc(n), out(n), X(n);
+        for (size_t r = 0; r < G; r++)
+          for (size_t j = 0; j < m; j++) loc[r * m + j] = h[r + G * j];
+        c.check(ronk_memcpy_h2d(c.get(), d, loc.data(), n * 8));
+        dist::ntt_virtual(c, P, 7, (uint64_t*)d, log_n, 1, log_g, flavour);
+        c.check(ronk_memcpy_d2h(c.get(), out.data(), d, n * 8));
+        for (size_t s2 = 0; s2 < G; s2++)
+          for (size_t q = 0; q < G; q++)
+            for (size_t k = 0; k < blk; k++) X[s2 * blk + k + m * q] = out[s2 * m + q * blk + k];
+        CHECK(X == ref);
+      }
+    }
     ronk_dev_free(c.get(), d); ronk_dev_free(c.get(), dp); ronk_dev_free(c.get(), ds);
     dist::finalize(c);
     CHECK(ronk_ntt_u64_dist(c.get(), P, 7, nullptr, 10, 1, 0) == RONK_ENCCL);   // no communicator any more
