@@ -230,10 +230,10 @@ static int launch3_ng(ronk_ctx* ctx, const F& f, const Ntt3Args& A, const char* 
 }
 template <class F, int PASS, bool INV, int LOGN, bool BOUNDED>
 static int launch3(ronk_ctx* ctx, const F& f, const Ntt3Args& A, const char* name, bool dependent) {
-  const unsigned tiles = A.batch * (LOGN == 24 ? 4096u : LOGN == 20 ? 256u : 16u);
+  const unsigned tiles = A.batch * (LOGN >= 21 ? (1u << (LOGN - 12)) : LOGN == 20 ? 256u : 16u);
   // a grid that leaves most warp slots empty runs one radix-16 group per thread (256 threads per tile): a single
   // 2^16- or 2^20-point transform is a chain of dependent carry chains per warp, and twice the warps halve it
-  if constexpr (LOGN != 24 && !BOUNDED) {
+  if constexpr ((LOGN == 16 || LOGN == 20) && !BOUNDED) {
     if (tiles < (unsigned)ctx->tune.ntt3_ng1_tiles * (unsigned)ctx->sm_count)
       return launch3_ng<F, PASS, INV, LOGN, BOUNDED, 1>(ctx, f, A, name, dependent, tiles);
   }
@@ -351,11 +351,11 @@ static int run_ntt3(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, c
   const int d = INV ? 1 : 0;
   const u64 n = (u64)1 << LOGN;
   RONK_TRY((ntt3_tables<F, INV>(ctx, f, pl, LOGN)));
-  if ((LOGN == 24 || LOGN == 20) && ctx->tune.ntt3_t1 && !pl.t1[d]) {  // n-word table of the stepped twiddles: 128 MiB (2^24) / 8 MiB (2^20) per direction; no memory: stay stepped
-    if (LOGN == 20 && (pl.log_n1 != 10 || !pl.tw_lo || !pl.tw2)) return set_err(ctx, RONK_ECUDA, "internal: unexpected 2^20 plan shape");
+  if (LOGN >= 20 && ctx->tune.ntt3_t1 && !pl.t1[d]) {  // n-word table of the stepped twiddles: 128 MiB (2^24) / 8 MiB (2^20) per direction; no memory: stay stepped
+    if (pl.log_n1 != (u32)(LOGN + 1) / 2 || !pl.tw_lo || !pl.tw2) return set_err(ctx, RONK_ECUDA, "internal: unexpected plan shape");
     if (cudaMalloc((void**)&pl.t1[d], n * sizeof(u64)) == cudaSuccess) {
       LaunchScope ls(ctx, "ntt3_t1");
-      if (LOGN == 24) ntt3_t1_kernel<F><<<(unsigned)(n / 256), 256, 0, ctx->stream>>>(f, pl.tw_lo, pl.tw2, INV ? 1 : 0, pl.t1[d]);
+      if (LOGN >= 21) ntt3_t1_kernel<F><<<(unsigned)(n / 256), 256, 0, ctx->stream>>>(f, pl.tw_lo, pl.tw2, INV ? 1 : 0, pl.t1[d], (u32)LOGN);
       else ntt3_t1_20_kernel<F><<<(unsigned)(n / 256), 256, 0, ctx->stream>>>(f, pl.tw_lo, pl.tw2, INV ? 1 : 0, pl.t1[d]);
     } else {
       cudaGetLastError();
@@ -365,7 +365,7 @@ static int run_ntt3(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, c
   }
   if (batch > (0x7FFFFFFFu >> 12)) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
   RONK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, ((size_t)batch << LOGN) * sizeof(u64)));
-  if (LOGN == 20 && (pl.log_n1 != 10 || !pl.tw_lo || !pl.tw2)) return set_err(ctx, RONK_ECUDA, "internal: unexpected 2^20 plan shape");
+  if (LOGN >= 20 && (pl.log_n1 != (u32)(LOGN + 1) / 2 || !pl.tw_lo || !pl.tw2)) return set_err(ctx, RONK_ECUDA, "internal: unexpected plan shape");
   Ntt3Args A = {};
   A.t1 = ctx->tune.ntt3_t1 ? pl.t1[d] : nullptr;
   A.tw256 = pl.tw256[d];
@@ -394,12 +394,12 @@ static int run_ntt3(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, c
     RONK_TRY((launch3c<F, INV>(ctx, f, A, INV ? "intt3_c" : "ntt3_c")));
     return check_launch(ctx, "ntt3 pass C");
   } else {
-    if constexpr (LOGN == 24) {
+    if constexpr (LOGN >= 21) {
       RONK_TRY((launch3<F, 1, INV, LOGN, BOUNDED>(ctx, f, A, INV ? "intt3_pass1" : "ntt3_pass1", false)));
       RONK_TRY(check_launch(ctx, "ntt3 pass 1"));
       A.src = (const u64*)ctx->ws;
     }
-    RONK_TRY((launch3<F, 2, INV, LOGN, BOUNDED && LOGN == 16>(ctx, f, A, INV ? "intt3_pass2" : "ntt3_pass2", LOGN == 24)));
+    RONK_TRY((launch3<F, 2, INV, LOGN, BOUNDED && LOGN == 16>(ctx, f, A, INV ? "intt3_pass2" : "ntt3_pass2", LOGN >= 21)));
     RONK_TRY(check_launch(ctx, "ntt3 pass 2"));
     A.src = (const u64*)ctx->ws;
     A.dst = data;
@@ -439,6 +439,11 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
       // 2^16: worth it once the grid fills the GPU (16 tiles per transform); single transforms stay launch-bound
       if (log_n == 24 && !bounded) return run_ntt3<F, INV, 24, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
       if (log_n == 24 && batch == 1) return run_ntt3<F, INV, 24, true>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
+      if (log_n >= 21 && log_n <= 23 && !bounded && ctx->tune.ntt3_mid) {   // 2^21 … 2^23: first pass of 32 / 64 / 128 points, then as 2^24
+        if (log_n == 21) return run_ntt3<F, INV, 21, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
+        if (log_n == 22) return run_ntt3<F, INV, 22, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
+        return run_ntt3<F, INV, 23, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
+      }
       if (log_n == 20 && !bounded && ctx->tune.ntt3_20) return run_ntt3<F, INV, 20, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
       if (log_n == 16 && !bounded && batch <= (u32)ctx->tune.ntt16_cluster_max_batch) {
         bool done = false;

@@ -85,6 +85,16 @@ constexpr u32 N3_TILE_WORDS = 16 * 272;  // 4352 words = 34 816 B
 RONK_HD constexpr u32 n3_word(u32 d1, u32 d0, u32 c) { return 272u * d1 + 17u * d0 + c; }
 RONK_HD constexpr u32 n3_br4(int j) { return (u32)(((j & 1) << 3) | ((j & 2) << 1) | ((j & 4) >> 1) | ((j & 8) >> 3)); }
 
+// n = 2^LOGN, 21 <= LOGN <= 24: first pass = R-point transforms with R = 2^(LOGN - 16) = 16·R0 (R0 = 2, 4, 8, 16); the
+// 256-row tile then holds 16 / R0 of them side by side (column blocks of 16), so the thread mapping, the tile layout and
+// passes 2 and 3 are those of the 2^24-point transform with 256 replaced by R in the strides.
+RONK_HD constexpr int n3_log_r0(int logn) { return logn >= 21 ? logn - 20 : 4; }
+RONK_HD constexpr u32 n3_brn(u32 v, int bits) {   // bit reversal of the low `bits` bits
+  u32 r = 0;
+  for (int i = 0; i < bits; i++) r |= ((v >> i) & 1u) << (bits - 1 - i);
+  return r;
+}
+
 struct Ntt3Args {
   const u64* src;
   u64* dst;
@@ -103,8 +113,11 @@ struct Ntt3Args {
 // ---- round 0: 16 elements per group straight from global memory ----
 // PASS 1, 2: group g ↔ (d0 = g >> 4, c = g & 15): element q is row i = 16 q + d0 of the tile, column c.
 // PASS 3:    group g ↔ (col = g >> 4, d0 = g & 15): element q is i = 16 q + d0 of column col (i is the contiguous axis).
-template <class F, int PASS, bool INV, bool BOUNDED = false, int NG = 2>
+// First pass of 2^21 … 2^23 (LR0 = log2 R0 < 4, PASS 1 only): register q = u·R0 + d1 is row 16·d1 + d0 of sub-transform u,
+// whose sixteen columns start 16·u after this thread's; radix_network<LR0> runs the 16 / R0 networks side by side.
+template <class F, int PASS, bool INV, bool BOUNDED = false, int NG = 2, int LR0 = 4>
 RONK_DEV void n3_round0(const F& f, u64* smem, const Ntt3Args& A, u64 tile_base, u64 row_stride, u64 col_stride, u32 tid) {
+  constexpr u32 R0 = 1u << LR0;
 #if RONK_NTT3_UNROLL_GROUPS == 1
 #pragma unroll 1
 #else
@@ -126,19 +139,25 @@ RONK_DEV void n3_round0(const F& f, u64* smem, const Ntt3Args& A, u64 tile_base,
     u64 x[16];
 #pragma unroll
     for (int q = 0; q < 16; q++) {
+      const u64 off = (u64)((u32)q & (R0 - 1u)) * 16u * row_stride + (u64)((u32)q >> LR0) * 16u * col_stride;  // LR0 = 4: q·16·row_stride
       if (BOUNDED) {
-        const u64 idx = tile_base + (u64)d0 * row_stride + (u64)c * col_stride + (u64)q * 16u * row_stride;
-        x[q] = idx < A.src_len ? p[(u64)q * 16u * row_stride] : 0;
+        const u64 idx = tile_base + (u64)d0 * row_stride + (u64)c * col_stride + off;
+        x[q] = idx < A.src_len ? p[off] : 0;
       } else {
-        x[q] = p[(u64)q * 16u * row_stride];
+        x[q] = p[off];
       }
     }
-    radix_network<4, INV>(f, x);
-    const u64* tw = A.tw256 + d0;  // ω_256^(d0·k_hi), k_hi = bitrev4(register index)
+    radix_network<LR0, INV>(f, x);
+    // ω_R^(d0·k_lo) = ω_256^(d0·k_lo·16/R0), k_lo = bitrev_LR0(register index mod R0); nothing to do where k_lo = 0
+    const u64* tw = A.tw256;
     u64* s = smem + n3_word(0, d0, c);
-    s[0] = x[0];
 #pragma unroll
-    for (int j = 1; j < 16; j++) s[n3_word((u32)j, 0, 0)] = f.mul_tw(x[j], ld_tw(tw + (n3_br4(j) - 1u) * d0));
+    for (int j = 0; j < 16; j++) {
+      constexpr u32 sc = 16u >> LR0;
+      const u32 kl = n3_brn((u32)j & (R0 - 1u), LR0);
+      if (kl == 0) s[n3_word((u32)j, 0, 0)] = x[j];
+      else s[n3_word((u32)j, 0, 0)] = f.mul_tw(x[j], ld_tw(tw + kl * sc * d0));
+    }
   }
 }
 
@@ -147,8 +166,11 @@ RONK_DEV void n3_round0(const F& f, u64* smem, const Ntt3Args& A, u64 tile_base,
 // 16·bitrev4(q) + bitrev4(d1); it goes to row k of the output view, column c.
 template <class F, int PASS, bool INV, bool BOUNDED = false, int LOGN = 24, int NG = 2>
 RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile_base, u64 row_stride, u32 m_base, u32 tid) {
-  constexpr u32 LO = (LOGN == 20) ? 10u : 12u;            // two-level twiddle tables: ω_n^x, x < 2^LO, and ω_n^(2^LO·y)
-  constexpr u32 EMASK = (LOGN == 20) ? 0xFFFFFu : 0xFFFFFFu;  // exponents mod n
+  constexpr u32 LO = (u32)(LOGN + 1) / 2u;                // two-level twiddle tables (the plan's split): ω_n^x, x < 2^LO, and ω_n^(2^LO·y)
+  constexpr u32 EMASK = (1u << LOGN) - 1u;                // exponents mod n
+  constexpr bool P1 = PASS == 1 && LOGN >= 21;            // first pass of 2^21 … 2^24: R = 16·R0 points, 16 / R0 column blocks per tile
+  constexpr int LR0 = P1 ? n3_log_r0(LOGN) : 4;
+  constexpr u32 R0 = 1u << LR0;
 #if RONK_NTT3_UNROLL_GROUPS == 1
 #pragma unroll 1
 #else
@@ -156,20 +178,22 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
 #endif
   for (int h = 0; h < NG; h++) {
     const u32 g = tid + (u32)h * N3_THREADS;
-    const u32 d1 = g >> 4, c = g & 15u;
-    const u32 b = bitrev(d1, 4);
-    const u64* s = smem + n3_word(d1, 0, c);
+    const u32 d1 = g >> 4, c0 = g & 15u;
+    // tile slot d1 = u·R0 + position of the round-0 register: column block u, low output digit b = bitrev(position)
+    const u32 b = bitrev(d1 & (R0 - 1u), LR0);
+    const u32 c = c0 + 16u * (d1 >> LR0);                 // column within the tile's 256 / R0 columns (LR0 = 4: c0)
+    const u64* s = smem + n3_word(d1, 0, c0);
 #if (RONK_NTT3_EARLY_TW & 1) && defined(__CUDA_ARCH__)
     // The table twiddles of this group are PREFETCHED (L1) before the shared-memory reads and the network: loaded where
     // they are used (the compiler keeps them behind the run-time `if (A.t1)`, and sinks even explicit early loads to save
     // registers), their DRAM latency was the top stall of pass 1 (ncu r02s: long_scoreboard 1.8 per issued instruction).
-    if (PASS == 1 && (LOGN == 24 || LOGN == 20)) {
+    if (PASS == 1 && (LOGN >= 21 || LOGN == 20)) {
       // no branch on A.t1 here (the compiler would merge it with the one below and sink the prefetches into it): without
       // a table the prefetches go to the sixteen lines this group is about to store to — valid, spread over the tile like
       // the table rows (one shared address for all threads measured 2× slower: every warp of the GPU on one L1 line)
-      const u64* t = A.t1 ? (LOGN == 24 ? A.t1 + ((u64)b << 16) + m_base + c : A.t1 + 16u * m_base + ((u64)b << 12) + c)
+      const u64* t = A.t1 ? (LOGN >= 21 ? A.t1 + ((u64)b << 16) + m_base + c : A.t1 + 16u * m_base + ((u64)b << 12) + c)
                           : A.dst + tile_base + (u64)b * row_stride + c;
-      const u64 st = A.t1 ? ((u64)1 << (LOGN == 24 ? 20 : 16)) : 16u * row_stride;
+      const u64 st = A.t1 ? (LOGN >= 21 ? ((u64)R0 << 16) : ((u64)1 << 16)) : (u64)R0 * row_stride;
 #pragma unroll
       for (int qp = 0; qp < 16; qp++) asm volatile("prefetch.global.L1 [%0];" ::"l"(t + (u64)qp * st) : "memory");
     }
@@ -193,15 +217,15 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
 #pragma unroll
     for (int q = 0; q < 16; q++) x[q] = s[n3_word(0, (u32)q, 0)];
     radix_network<4, INV>(f, x);
-    u64* o = A.dst + tile_base + (u64)b * row_stride + c;   // row k = 16 q' + b, q' = bitrev4(register index)
-    if (PASS == 1 && LOGN == 24 && A.t1) {
+    u64* o = A.dst + tile_base + (u64)b * row_stride + c;   // row k = R0 q' + b, q' = bitrev4(register index) (R0 = 16 unless first pass of 2^21 … 2^23)
+    if (PASS == 1 && LOGN >= 21 && A.t1) {
       // ω_n^(±k1·m) from the n-word table [k1][m]: the same offsets as the stores, one coalesced load each
       const u64* t = A.t1 + ((u64)b << 16) + m_base + c;
       u64 w[16];
 #pragma unroll
-      for (int qp = 0; qp < 16; qp++) w[qp] = ld_tw(t + ((u64)qp << 20));
+      for (int qp = 0; qp < 16; qp++) w[qp] = ld_tw(t + (u64)qp * ((u64)R0 << 16));
 #pragma unroll
-      for (int qp = 0; qp < 16; qp++) o[(u64)qp * 16u * row_stride] = f.mul_tw(x[n3_br4(qp)], w[qp]);
+      for (int qp = 0; qp < 16; qp++) o[(u64)qp * R0 * row_stride] = f.mul_tw(x[n3_br4(qp)], w[qp]);
     } else if (PASS == 1 && LOGN == 20 && A.t1) {
       // pass A2 of 2^20: ω_n^(±j1·k2) from the n-word table indexed like this pass's output (16·k2 + j1)
       const u64* t = A.t1 + 16u * m_base + ((u64)b << 12) + c;
@@ -213,8 +237,9 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
     } else if (PASS == 1) {
       // ω_n^(±k1·m), m = 256 j2 + j3 (this thread's column), k1 = 16 q' + b: stepped over q' with ρ = ω_n^(±16 m)
       // 2^20 (pass A2): ω_n^(j1·k2), j1 = c (this thread's column), k2 = m_base + 256·(16 q' + b): ρ = ω_n^(4096 c)
+      // first pass of 2^21 … 2^23: k1 = R0 q' + b, ρ = ω_n^(±R0 m)
       const u32 m = m_base + c;
-      u32 ex0 = (LOGN == 20) ? c * (m_base + 256u * b) : m * b, exd = (LOGN == 20) ? (c << 12) : (m << 4);
+      u32 ex0 = (LOGN == 20) ? c * (m_base + 256u * b) : m * b, exd = (LOGN == 20) ? (c << 12) : (m * R0);
       if (INV) { ex0 = (0u - ex0) & EMASK; exd = (0u - exd) & EMASK; }
       u64 w = f.mul_tw(ld_tw(A.tw_lo + (ex0 & ((1u << LO) - 1u))), ld_tw(A.tw_hi + (ex0 >> LO)));
       const u64 rho = f.mul_tw(ld_tw(A.tw_lo + (exd & ((1u << LO) - 1u))), ld_tw(A.tw_hi + (exd >> LO)));
@@ -224,14 +249,14 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
       u64 w1 = f.mul_tw(w, rho);
 #pragma unroll
       for (int qp = 0; qp < 16; qp += 2) {
-        o[(u64)qp * 16u * row_stride] = f.mul_tw(x[n3_br4(qp)], w);
-        o[(u64)(qp + 1) * 16u * row_stride] = f.mul_tw(x[n3_br4(qp + 1)], w1);
+        o[(u64)qp * R0 * row_stride] = f.mul_tw(x[n3_br4(qp)], w);
+        o[(u64)(qp + 1) * R0 * row_stride] = f.mul_tw(x[n3_br4(qp + 1)], w1);
         if (qp < 14) { w = f.mul_tw(w, rho2); w1 = f.mul_tw(w1, rho2); }
       }
 #else
 #pragma unroll
       for (int qp = 0; qp < 16; qp++) {
-        o[(u64)qp * 16u * row_stride] = f.mul_tw(x[n3_br4(qp)], w);
+        o[(u64)qp * R0 * row_stride] = f.mul_tw(x[n3_br4(qp)], w);
         if (qp < 15) w = f.mul_tw(w, rho);
       }
 #endif
@@ -335,24 +360,33 @@ RONK_DEV void n3_tile_geometry(u32 tile, u64* in_base, u64* in_row, u64* in_col,
     }
     return;
   }
-  const u64 b = tile >> 12;
-  const u32 hi = (tile >> 4) & 255u, lo = tile & 15u;
-  if (PASS == 1) {        // hi = j2, lo = s
-    *in_base = *out_base = (b << 24) + ((u64)hi << 8) + 16u * lo;
+  // LOGN = 21 … 24: R = 2^(LOGN-16) rows in pass 1 (R = 256 at 2^24), n / 4096 tiles per transform in every pass:
+  //   pass 1: tile t: rows j1 (stride 65536), columns m = (4096 / R)·t + …  (16 / R0 column blocks of 16)   — in = out view
+  //   pass 2: tile (k1 = t >> 4, s = t & 15): rows j2 (stride 256), columns j3 = 16 s + c                    — in = out view
+  //   pass 3: tile (k2 = t / (R/16), tt): input column col ↔ k1 = 16 tt + col (stride 65536), i = j3 contiguous;
+  //           output X[k1 + R k2 + 256 R k3]: rows k3 (stride 256 R), columns k1
+  constexpr int L = LOGN >= 21 ? LOGN : 24;   // (the two small sizes returned above; keeps their dead code well-formed)
+  const u64 b = tile >> (L - 12);
+  const u32 t = tile & ((1u << (L - 12)) - 1u);
+  if (PASS == 1) {
+    const u32 mb = t << (24 - L + 4);   // (4096 / R) columns per tile
+    *in_base = *out_base = (b << L) + mb;
     *in_row = *out_row = 65536;
     *in_col = 1;
-    *m_base = (hi << 8) + 16u * lo;
-  } else if (PASS == 2) { // hi = k1, lo = s
-    *in_base = *out_base = (b << 24) + ((u64)hi << 16) + 16u * lo;
+    *m_base = mb;
+  } else if (PASS == 2) {
+    const u32 hi = t >> 4, lo = t & 15u;   // hi = k1, lo = s
+    *in_base = *out_base = (b << L) + ((u64)hi << 16) + 16u * lo;
     *in_row = *out_row = 256;
     *in_col = 1;
     *m_base = 16u * lo;
-  } else {                // hi = k2, lo = t
-    *in_base = (b << 24) + ((u64)(16u * lo) << 16) + ((u64)hi << 8);
+  } else {
+    const u32 hi = t >> (L - 20), lo = t & ((1u << (L - 20)) - 1u);   // hi = k2, lo = tt
+    *in_base = (b << L) + ((u64)(16u * lo) << 16) + ((u64)hi << 8);
     *in_row = 1;
     *in_col = 65536;
-    *out_base = (b << 24) + ((u64)hi << 8) + 16u * lo;
-    *out_row = 65536;
+    *out_base = (b << L) + ((u64)hi << (L - 16)) + 16u * lo;
+    *out_row = (u64)1 << (L - 8);
     *m_base = 0;
   }
 }
@@ -388,7 +422,8 @@ __global__ void __launch_bounds__(N3_THREADS * (2 / NG), RONK_NTT3_MINB / (2 / N
   // not touch the predecessor's output before griddepcontrol.wait (no-ops without the launch attribute)
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  n3_round0<F, PASS, INV, BOUNDED && PASS == (LOGN == 24 ? 1 : 2), NG>(f, smem, A, in_base, in_row, in_col, tid);  // src_len: first pass only
+  n3_round0<F, PASS, INV, BOUNDED && PASS == (LOGN >= 21 ? 1 : 2), NG, (PASS == 1 && LOGN >= 21) ? n3_log_r0(LOGN) : 4>(
+      f, smem, A, in_base, in_row, in_col, tid);  // src_len: first pass only
   __syncthreads();
   n3_round1<F, PASS, INV, BOUNDED, LOGN, NG>(f, smem, A, out_base, out_row, m_base, tid);
 }
@@ -443,12 +478,13 @@ __global__ void __launch_bounds__(N3C_THREADS) ntt3c_kernel(const F f, const Ntt
 
 // T1[k1][m] = ω_n^(±k1·m), k1 < 256, m < 65536 (twiddle form), from the two-level tables
 template <class F>
-__global__ void ntt3_t1_kernel(const F f, const u64* __restrict__ tw_lo, const u64* __restrict__ tw_hi, int inverse, u64* __restrict__ out) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;  // < 2^24
-  const u32 k1 = i >> 16, m = i & 0xFFFFu;
-  u32 ex = (k1 * m) & 0xFFFFFFu;
-  if (inverse) ex = (0u - ex) & 0xFFFFFFu;
-  out[i] = f.mul_tw(tw_lo[ex & 4095u], tw_hi[ex >> 12]);
+__global__ void ntt3_t1_kernel(const F f, const u64* __restrict__ tw_lo, const u64* __restrict__ tw_hi, int inverse, u64* __restrict__ out,
+                               u32 log_n) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;  // < n = 2^log_n, 21 <= log_n <= 24; two-level tables split at ceil(log_n / 2)
+  const u32 k1 = i >> 16, m = i & 0xFFFFu, mask = (1u << log_n) - 1u, lo = (log_n + 1u) / 2u;
+  u32 ex = (k1 * m) & mask;
+  if (inverse) ex = (0u - ex) & mask;
+  out[i] = f.mul_tw(tw_lo[ex & ((1u << lo) - 1u)], tw_hi[ex >> lo]);
 }
 
 // 2^20: T1[16·k2 + j1] = ω_n^(±j1·k2), k2 < 65536, j1 < 16 — indexed like the output of pass A2 (10 / 10 two-level tables)

@@ -202,7 +202,7 @@ int g_ntt3_ng1 = 0;  // 1: the 256-thread (one group per thread) flavour of the 
 template <class F, int PASS, bool INV, int LOGN, bool BOUNDED = false>
 void run_pass3(const F& f, const Ntt3Args& A) {
   std::vector<u64> smem(N3_TILE_WORDS);
-  for (u32 tile = 0; tile < A.batch * (LOGN == 24 ? 4096u : LOGN == 20 ? 256u : 16u); tile++) {
+  for (u32 tile = 0; tile < A.batch * (LOGN >= 21 ? (1u << (LOGN - 12)) : LOGN == 20 ? 256u : 16u); tile++) {
     u64 in_base, in_row, in_col, out_base, out_row;
     u32 m_base;
     n3_tile_geometry<PASS, LOGN>(tile, &in_base, &in_row, &in_col, &out_base, &out_row, &m_base);
@@ -211,7 +211,8 @@ void run_pass3(const F& f, const Ntt3Args& A) {
       for (u32 t = 0; t < 2 * N3_THREADS; t++) n3_round1<F, PASS, INV, false, LOGN, 1>(f, smem.data(), A, out_base, out_row, m_base, t);
       continue;
     }
-    for (u32 t = 0; t < N3_THREADS; t++) n3_round0<F, PASS, INV, BOUNDED && PASS == (LOGN == 24 ? 1 : 2)>(f, smem.data(), A, in_base, in_row, in_col, t);
+    for (u32 t = 0; t < N3_THREADS; t++)
+      n3_round0<F, PASS, INV, BOUNDED && PASS == (LOGN >= 21 ? 1 : 2), 2, (PASS == 1 && LOGN >= 21) ? n3_log_r0(LOGN) : 4>(f, smem.data(), A, in_base, in_row, in_col, t);
     for (u32 t = 0; t < N3_THREADS; t++) n3_round1<F, PASS, INV, BOUNDED, LOGN>(f, smem.data(), A, out_base, out_row, m_base, t);
   }
 }
@@ -225,15 +226,16 @@ int run3(const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 batch, const u
   if (INV) w = h_powmod(w, p - 2, p);
   auto tw256 = table(f, h_powmod(w, n >> 8, p), 1, 256);
   std::vector<u64> tw_lo, tw_hi, t1;
-  if (LOGN == 24) {
-    tw_lo = table(f, wf, 1, 4096);                       // forward tables; the kernel negates exponents for INV
-    tw_hi = table(f, h_powmod(wf, 4096, p), 1, 4096);
+  if (LOGN >= 21) {                                      // the plan's two-level tables, split at ceil(LOGN / 2)
+    const u32 lo = (u32)(LOGN + 1) / 2u, mask = (1u << LOGN) - 1u;
+    tw_lo = table(f, wf, 1, 1u << lo);                   // forward tables; the kernel negates exponents for INV
+    tw_hi = table(f, h_powmod(wf, (u64)1 << lo, p), 1, 1u << (LOGN - lo));
     if (g_ntt3_t1) {                                     // mirrors ntt3_t1_kernel
       t1.resize(n);
       for (u64 i = 0; i < n; i++) {
-        u32 ex = (u32)((i >> 16) * (i & 0xFFFFu)) & 0xFFFFFFu;
-        if (INV) ex = (0u - ex) & 0xFFFFFFu;
-        t1[i] = f.mul_tw(tw_lo[ex & 4095u], tw_hi[ex >> 12]);
+        u32 ex = (u32)((i >> 16) * (i & 0xFFFFu)) & mask;
+        if (INV) ex = (0u - ex) & mask;
+        t1[i] = f.mul_tw(tw_lo[ex & ((1u << lo) - 1u)], tw_hi[ex >> lo]);
       }
     }
   }
@@ -269,7 +271,7 @@ int run3(const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 batch, const u
       for (u64 k2 = 0; k2 < 65536; k2++) n3c_point<F, INV>(f, A, b, k2);
     return 0;
   }
-  if (LOGN == 24) {
+  if (LOGN >= 21) {
     run_pass3<F, 1, INV, LOGN, BOUNDED>(f, A);
     A.src = ws.data();
   }
@@ -396,6 +398,12 @@ int emu_ntt3(uint64_t* data, const uint64_t* mul, uint32_t log_n, uint32_t batch
     return inverse ? run3<GoldilocksField, true, 16>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 16>(f, GL_P, 7, data, mul, batch);
   if (log_n == 20)
     return inverse ? run3<GoldilocksField, true, 20>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 20>(f, GL_P, 7, data, mul, batch);
+  if (log_n == 21)
+    return inverse ? run3<GoldilocksField, true, 21>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 21>(f, GL_P, 7, data, mul, batch);
+  if (log_n == 22)
+    return inverse ? run3<GoldilocksField, true, 22>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 22>(f, GL_P, 7, data, mul, batch);
+  if (log_n == 23)
+    return inverse ? run3<GoldilocksField, true, 23>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 23>(f, GL_P, 7, data, mul, batch);
   return 1;
 }
 // a batch of 2^16-point transforms through the cluster formulation (ntt16c_kernel), in place

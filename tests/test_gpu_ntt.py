@@ -441,3 +441,41 @@ def test_virtual_rank_distributed_transform(log_g):
                     for q in range(G):
                         X[s * blk + m * q: s * blk + m * q + blk] = out[s, b, q]
                 assert np.array_equal(X, want[b]), (p, log_n, batch, flavour, b)
+
+
+@pytest.mark.parametrize("log_n,batch", [(21, 2), (22, 1), (23, 1)])
+def test_mid_sizes_through_the_tile_kernels(log_n, batch):
+    """2^21 … 2^23 through the 256-point-tile kernels (first pass of 32 / 64 / 128 points, passes 2 and 3 as for 2^24):
+    bit-exact against the oracle, fused multiply, inverse round trip, and bit-for-bit agreement with the two-pass
+    tile kernel (RONK_NTT3_MID=0) and with the stepped first-pass twiddle (RONK_NTT3_T1=0)."""
+    import os
+    import torch
+    from ronkathon_b200 import Context, ops
+    c0 = ctx()
+    n = 1 << log_n
+    a = oracle.splitmix(GL, 500 + log_n, n * batch)
+    m = oracle.splitmix(GL, 510 + log_n, n * batch)
+    x = dev(a)
+    ops.ntt_(c0, x, log_n, batch)
+    X = host(x)
+    for b in range(batch):
+        assert np.array_equal(X[b * n:(b + 1) * n], oracle.ntt_fast(GL, a[b * n:(b + 1) * n])), b
+    y = dev(a)
+    ops.ntt_mul_(c0, y, dev(m), log_n, batch)
+    assert np.array_equal(host(y), oracle.vec_mul(GL, X, m))
+    ops.ntt_(c0, x, log_n, batch, inverse=True)
+    assert np.array_equal(host(x), a)
+    for env in ("RONK_NTT3_MID", "RONK_NTT3_T1"):
+        os.environ[env] = "0"
+        try:
+            c1 = Context(0, torch.cuda.current_stream().cuda_stream)
+        finally:
+            os.environ.pop(env)
+        z = dev(a)
+        ops.ntt_(c1, z, log_n, batch)
+        c1.sync()
+        assert np.array_equal(host(z), X), env
+        ops.ntt_(c1, z, log_n, batch, inverse=True)
+        c1.sync()
+        assert np.array_equal(host(z), a), env
+        c1.close()

@@ -335,6 +335,24 @@ def test_2_16_cluster_formulation_in_place(emu):
     assert np.array_equal(X, a)
 
 
+@pytest.mark.parametrize("log_n,t1_table", [(21, 0), (21, 1), (22, 1), (22, 0), (23, 1)])
+def test_mid_sizes_first_pass_of_32_64_128_points(emu, log_n, t1_table):
+    """2^21 … 2^23: the first pass is an R = 2^(log n - 16)-point transform (radix R/16, then radix 16; 16·16/R of them side by
+    side in a tile), passes 2 and 3 are those of 2^24 with R in the strides: forward against the oracle, fused
+    multiply, inverse; first-pass twiddles stepped (0) or from the n-word table (1)."""
+    n = 1 << log_n
+    a = oracle.splitmix(GL, 60 + log_n, n)
+    m = oracle.splitmix(GL, 70 + log_n, n)
+    X = a.copy()
+    assert emu.emu_ntt3(_ptr(X), None, log_n, 1, 0, t1_table) == 0
+    assert np.array_equal(X, oracle.ntt_fast(GL, a))
+    Y = a.copy()
+    assert emu.emu_ntt3(_ptr(Y), _ptr(m), log_n, 1, 0, t1_table) == 0
+    assert np.array_equal(Y, oracle.vec_mul(GL, X, m))
+    assert emu.emu_ntt3(_ptr(X), None, log_n, 1, 1, t1_table) == 0
+    assert np.array_equal(X, a)
+
+
 @pytest.mark.parametrize("t1_table", [0, 1])
 def test_2_20_as_sixteen_interleaved_2_16_transforms_plus_radix16(emu, t1_table):
     """2^20 (BASELINE config 2) = passes A1 / A2 of the tile kernel on 16 interleaved 2^16-point transforms + the
