@@ -285,7 +285,7 @@ static int ntt3_tables(ronk_ctx* ctx, const F& f, NttPlan& pl, int log_n) {
 // when the device refuses the cluster shape (the caller then takes the two-launch path).
 template <class F, bool INV>
 static int run_ntt16_cluster(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, const u64* src, const u64* mul, u32 batch,
-                             bool* done) {
+                             bool* done, u64 mul_mask = ~0ULL) {
   NttPlan& pl = const_cast<NttPlan&>(pl_c);
   *done = false;
   if (ctx->cluster16_state < 0) return RONK_OK;
@@ -310,6 +310,7 @@ static int run_ntt16_cluster(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64
   A.src = src;
   A.dst = data;
   A.mul_src = mul;
+  A.mul_mask = mul_mask;
   A.flags = mul ? NTT_FLAG_MUL : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(16u * batch);
@@ -346,7 +347,7 @@ static int run_ntt16_cluster(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64
 // written by the last pass, so src == data (in place) and a short data buffer (dst_len words) are both fine.
 template <class F, bool INV, int LOGN, bool BOUNDED>
 static int run_ntt3(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, const u64* src, const u64* mul, u32 batch,
-                    u64 src_len, u64 dst_len) {
+                    u64 src_len, u64 dst_len, u64 mul_mask = ~0ULL) {
   NttPlan& pl = const_cast<NttPlan&>(pl_c);
   const int d = INV ? 1 : 0;
   const u64 n = (u64)1 << LOGN;
@@ -375,6 +376,7 @@ static int run_ntt3(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, c
   A.batch = batch;
   A.src_len = src_len;
   A.dst_len = dst_len;
+  A.mul_mask = mul_mask;
   A.src = src;
   A.dst = (u64*)ctx->ws;
   if constexpr (LOGN == 20) {
@@ -434,24 +436,24 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
     return launch_tile<F, MODE_SINGLE, INV>(ctx, f, A, (u32)tiles, INV ? "intt_single" : "ntt_single");
   }
   if constexpr (std::is_same<F, GoldilocksField>::value) {
-    if (ctx->tune.ntt3 && mul_mask == ~0ULL && !(INV && mul)) {
+    if (ctx->tune.ntt3 && !(INV && mul)) {   // mul_mask: one multiplier word per output (~0) or a shared n-word one (n - 1)
       const bool bounded = src_len != NTT_UNBOUNDED || dst_len != NTT_UNBOUNDED;  // only ever with batch == 1
       // 2^16: worth it once the grid fills the GPU (16 tiles per transform); single transforms stay launch-bound
-      if (log_n == 24 && !bounded) return run_ntt3<F, INV, 24, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
-      if (log_n == 24 && batch == 1) return run_ntt3<F, INV, 24, true>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
+      if (log_n == 24 && !bounded) return run_ntt3<F, INV, 24, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
+      if (log_n == 24 && batch == 1) return run_ntt3<F, INV, 24, true>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
       if (log_n >= 21 && log_n <= 23 && !bounded && ctx->tune.ntt3_mid) {   // 2^21 … 2^23: first pass of 32 / 64 / 128 points, then as 2^24
-        if (log_n == 21) return run_ntt3<F, INV, 21, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
-        if (log_n == 22) return run_ntt3<F, INV, 22, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
-        return run_ntt3<F, INV, 23, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
+        if (log_n == 21) return run_ntt3<F, INV, 21, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
+        if (log_n == 22) return run_ntt3<F, INV, 22, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
+        return run_ntt3<F, INV, 23, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
       }
-      if (log_n == 20 && !bounded && ctx->tune.ntt3_20) return run_ntt3<F, INV, 20, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
+      if (log_n == 20 && !bounded && ctx->tune.ntt3_20) return run_ntt3<F, INV, 20, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
       if (log_n == 16 && !bounded && batch <= (u32)ctx->tune.ntt16_cluster_max_batch) {
         bool done = false;
-        RONK_TRY((run_ntt16_cluster<F, INV>(ctx, f, pl, data, src, mul, batch, &done)));
+        RONK_TRY((run_ntt16_cluster<F, INV>(ctx, f, pl, data, src, mul, batch, &done, mul_mask)));
         if (done) return RONK_OK;
       }
       if (log_n == 16 && !bounded && batch >= (u32)ctx->tune.ntt3_min_batch16)
-        return run_ntt3<F, INV, 16, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len);
+        return run_ntt3<F, INV, 16, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
     }
   }
   const size_t bytes = ((size_t)batch << log_n) * sizeof(u64);

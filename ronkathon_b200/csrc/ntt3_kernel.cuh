@@ -103,7 +103,9 @@ struct Ntt3Args {
   const u64* tw_hi;    // pass 1: ω_n^(4096 y), y < 4096
   const u64* t2;       // pass 2: ω_65536^(±k2·j3) [· n^-1 for the inverse], [k2][j3], twiddle form
   const u64* t1;       // pass 1, optional: ω_n^(±k1·m) as an n-word table [k1][m] (else stepped from tw_lo / tw_hi)
-  const u64* mul_src;  // pass 3, optional: point-wise multiplier indexed like the output
+  const u64* mul_src;  // pass 3, optional: point-wise multiplier indexed like the output …
+  u64 mul_mask;        // … modulo this mask + 1: ~0 = one multiplier per output word, n - 1 = ONE n-word multiplier shared by
+                       // every transform of the batch (the twiddle column of the distributed transform)
   u64 src_len;         // BOUNDED kernels (batch = 1): the first pass reads src[0, src_len) zero-extended,
   u64 dst_len;         //                               the last pass stores dst[0, dst_len) only
   u32 batch;
@@ -201,7 +203,7 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
 #if (RONK_NTT3_EARLY_TW & 8) && defined(__CUDA_ARCH__)
     if (PASS == 3) {   // the point-wise multiplier rows of the fused product (poly_mul), same idea and same select trick
       const bool fm = (A.flags & NTT_FLAG_MUL) != 0;
-      const u64* t = (fm ? A.mul_src : (const u64*)A.dst) + tile_base + (u64)b * row_stride + c;
+      const u64* t = fm ? A.mul_src + ((tile_base + (u64)b * row_stride + c) & A.mul_mask) : (const u64*)A.dst + tile_base + (u64)b * row_stride + c;
 #pragma unroll
       for (int qp = 0; qp < 16; qp++) asm volatile("prefetch.global.L1 [%0];" ::"l"(t + (u64)qp * 16u * row_stride) : "memory");
     }
@@ -272,7 +274,7 @@ RONK_DEV void n3_round1(const F& f, const u64* smem, const Ntt3Args& A, u64 tile
     } else {
       const u64 idx0 = tile_base + (u64)b * row_stride + c;   // index of row q' = 0 within the transform (BOUNDED: batch = 1)
       if (A.flags & NTT_FLAG_MUL) {
-        const u64* mp = A.mul_src + tile_base + (u64)b * row_stride + c;
+        const u64* mp = A.mul_src + (idx0 & A.mul_mask);   // a tile never straddles two transforms: the row offsets stay inside
         u64 w[16];
 #pragma unroll
         for (int qp = 0; qp < 16; qp++) w[qp] = mp[(u64)qp * 16u * row_stride];
@@ -401,7 +403,7 @@ RONK_DEV void n3c_point(const F& f, const Ntt3Args& A, u64 b, u64 k2) {
   radix_network<4, INV>(f, x);
   u64* o = A.dst + (b << 20) + k2;
   if (A.flags & NTT_FLAG_MUL) {
-    const u64* mp = A.mul_src + (b << 20) + k2;
+    const u64* mp = A.mul_src + (((b << 20) + k2) & A.mul_mask);
 #pragma unroll
     for (int q = 0; q < 16; q++) o[(u64)n3_br4(q) << 16] = f.mul(x[q], mp[(u64)n3_br4(q) << 16]);
   } else {

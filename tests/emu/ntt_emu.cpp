@@ -197,6 +197,7 @@ int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 l
   return 0;
 }
 
+unsigned long long g_ntt3_mul_mask = ~0ULL;  // n - 1: the multiplier is ONE n-word table shared by the whole batch
 int g_ntt3_ng1 = 0;  // 1: the 256-thread (one group per thread) flavour of the 2^16 / 2^20 tile passes
 // The three-pass 2^24 transform (ntt3_kernel.cuh), phase by phase like ntt3_kernel; tables as run_ntt3() builds them.
 template <class F, int PASS, bool INV, int LOGN, bool BOUNDED = false>
@@ -259,7 +260,7 @@ int run3(const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 batch, const u
   Ntt3Args A = {};
   A.tw256 = tw256.data(); A.tw_lo = tw_lo.data(); A.tw_hi = tw_hi.data(); A.t2 = t2.data(); A.batch = batch;
   A.t1 = t1.empty() ? nullptr : t1.data();
-  A.src_len = src_len; A.dst_len = dst_len;
+  A.src_len = src_len; A.dst_len = dst_len; A.mul_mask = g_ntt3_mul_mask;
   A.src = src ? src : data; A.dst = ws.data();          // the flow of run_ntt3(): src → ws, ws in place, ws → data
   if constexpr (LOGN == 20) {                            // A1 src → data, A2 data → ws, C ws → data
     A.dst = data;
@@ -297,7 +298,7 @@ int run16_cluster(const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 batch
   std::vector<u64> t2(65536);
   for (u32 i = 0; i < 65536; i++) t2[i] = f.to_tw(f.mul(field_pow(f, w, (u64)((i >> 8) * (i & 255u))), ninv));
   Ntt3Args A = {};
-  A.tw256 = tw256.data(); A.t2 = t2.data(); A.batch = batch; A.src_len = A.dst_len = ~0ULL;
+  A.tw256 = tw256.data(); A.t2 = t2.data(); A.batch = batch; A.src_len = A.dst_len = ~0ULL; A.mul_mask = ~0ULL;
   A.src = data; A.dst = data; A.mul_src = mul; A.flags = mul ? NTT_FLAG_MUL : 0;
   for (u32 b = 0; b < batch; b++) {
     std::vector<std::vector<u64>> tile(16, std::vector<u64>(N3_TILE_WORDS)), recv(16, std::vector<u64>(N3_RECV_WORDS));
@@ -405,6 +406,13 @@ int emu_ntt3(uint64_t* data, const uint64_t* mul, uint32_t log_n, uint32_t batch
   if (log_n == 23)
     return inverse ? run3<GoldilocksField, true, 23>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 23>(f, GL_P, 7, data, mul, batch);
   return 1;
+}
+// forward transforms ⊙ ONE n-word multiplier shared by the batch (the twiddle column of the distributed transform)
+int emu_ntt3_shared_mul(uint64_t* data, const uint64_t* mul_n_words, uint32_t log_n, uint32_t batch) {
+  g_ntt3_mul_mask = ((unsigned long long)1 << log_n) - 1;
+  const int rc = emu_ntt3(data, mul_n_words, log_n, batch, 0, 1);
+  g_ntt3_mul_mask = ~0ULL;
+  return rc;
 }
 // a batch of 2^16-point transforms through the cluster formulation (ntt16c_kernel), in place
 int emu_ntt16_cluster(uint64_t* data, const uint64_t* mul, uint32_t batch, int inverse) {

@@ -423,7 +423,7 @@ def test_virtual_rank_distributed_transform(log_g):
     from ronkathon_b200 import dist as rd
     c = ctx()
     G = 1 << log_g
-    cases = [(GL, 7, max(2 * log_g, 4), 1), (GL, 7, 12, 3), (GL, 7, 16 + log_g, 2), (GL, 7, 20, 1),
+    cases = [(GL, 7, max(2 * log_g, 4), 1), (GL, 7, 12, 3), (GL, 7, 16 + log_g, 2), (GL, 7, 20, 1), (GL, 7, 21 + log_g, 1),
              (2013265921, 31, 10, 2), (GL, pow(7, 5, GL), 12, 2)]
     for p, g, log_n, batch in cases:
         n, m = 1 << log_n, (1 << log_n) // G

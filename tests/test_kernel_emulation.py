@@ -38,6 +38,7 @@ def emu():
     lib.emu_ntt3.argtypes = [P64, P64, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
     lib.emu_ntt3_bounded.argtypes = [P64, C.c_uint64, P64, C.c_uint64, P64, C.c_int]
     lib.emu_ntt16_cluster.argtypes = [P64, P64, C.c_uint32, C.c_int]
+    lib.emu_ntt3_shared_mul.argtypes = [P64, P64, C.c_uint32, C.c_uint32]
     return lib
 
 
@@ -333,6 +334,19 @@ def test_2_16_cluster_formulation_in_place(emu):
     assert np.array_equal(Y, oracle.vec_mul(GL, X, m))
     assert emu.emu_ntt16_cluster(_ptr(X), None, batch, 1) == 0
     assert np.array_equal(X, a)
+
+
+@pytest.mark.parametrize("log_n,batch", [(16, 3), (20, 2), (21, 2)])
+def test_shared_multiplier_of_a_batch(emu, log_n, batch):
+    """The fused point-wise multiply with ONE n-word multiplier for the whole batch (mask n - 1 on the multiplier
+    index): what the distributed transform uses to put its twiddle column into the local transforms' store phase."""
+    n = 1 << log_n
+    a = oracle.splitmix(GL, 80 + log_n, n * batch)
+    m = oracle.splitmix(GL, 90 + log_n, n)
+    X = a.copy()
+    assert emu.emu_ntt3_shared_mul(_ptr(X), _ptr(m), log_n, batch) == 0
+    for b in range(batch):
+        assert np.array_equal(X[b * n:(b + 1) * n], oracle.vec_mul(GL, oracle.ntt_fast(GL, a[b * n:(b + 1) * n]), m)), b
 
 
 @pytest.mark.parametrize("log_n,t1_table", [(21, 0), (21, 1), (22, 1), (22, 0), (23, 1)])
