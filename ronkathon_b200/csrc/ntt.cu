@@ -446,6 +446,11 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
         if (log_n == 22) return run_ntt3<F, INV, 22, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
         return run_ntt3<F, INV, 23, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
       }
+      if (log_n >= 21 && log_n <= 23 && bounded && batch == 1 && ctx->tune.ntt3_mid) {   // zero-padded source / clipped destination (poly_mul)
+        if (log_n == 21) return run_ntt3<F, INV, 21, true>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
+        if (log_n == 22) return run_ntt3<F, INV, 22, true>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
+        return run_ntt3<F, INV, 23, true>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
+      }
       if (log_n == 20 && !bounded && ctx->tune.ntt3_20) return run_ntt3<F, INV, 20, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
       if (log_n == 16 && !bounded && batch <= (u32)ctx->tune.ntt16_cluster_max_batch) {
         bool done = false;

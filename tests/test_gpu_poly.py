@@ -223,6 +223,35 @@ def test_config3_poly_mul_2_24():
     assert np.array_equal(ec, oracle.vec_mul(GL, ea, eb))
 
 
+@pytest.mark.parametrize("la,lb", [((1 << 20) + 7, (1 << 19) + 1), ((1 << 21) - 5, 1 << 21), ((1 << 22) - 1, (1 << 22) - 3)])
+def test_poly_mul_mid_sizes_identity_and_agreement(la, lb):
+    """Products whose transforms have 2^21, 2^22 and 2^23 points: zero padding and clipping happen inside the bounded first /
+    last tile passes.  c(x) = a(x)·b(x) at a point (oracle Horner), end coefficients, length — and bit-for-bit
+    agreement with a context that keeps the two-pass kernel for these sizes (RONK_NTT3_MID=0)."""
+    import os
+    import torch
+    from ronkathon_b200 import Context, ops
+    c = ctx()
+    a = ops.splitmix_fill(c, la, 142, GL)
+    b = ops.splitmix_fill(c, lb, 143, GL)
+    prod = ops.poly_mul(c, a, b)
+    ah, bh, ph = host(a), host(b), host(prod)
+    assert len(ph) == la + lb - 1
+    assert int(ph[0]) == oracle.mul(GL, int(ah[0]), int(bh[0]))
+    assert int(ph[-1]) == oracle.mul(GL, int(ah[-1]), int(bh[-1]))
+    x = 0x0FEDCBA987654321 % GL
+    assert oracle.poly_eval_horner(GL, ph, x) == oracle.mul(GL, oracle.poly_eval_horner(GL, ah, x), oracle.poly_eval_horner(GL, bh, x))
+    os.environ["RONK_NTT3_MID"] = "0"
+    try:
+        c1 = Context(0, torch.cuda.current_stream().cuda_stream)
+    finally:
+        os.environ.pop("RONK_NTT3_MID")
+    p1 = ops.poly_mul(c1, a, b)
+    c1.sync()
+    assert np.array_equal(host(p1), ph)
+    c1.close()
+
+
 def test_evaluate_vs_oracle(gold64):
     from ronkathon_b200 import GoldilocksField, Polynomial, ops
     c = ctx()
