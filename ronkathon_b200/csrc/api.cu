@@ -47,6 +47,8 @@ int ronk_ctx_create(ronk_ctx** out, int device, void* stream) {
   ctx->tune.ntt3_t1 = env_int("RONK_NTT3_T1", 1);
   ctx->tune.ntt3_20 = env_int("RONK_NTT3_20", 1);
   ctx->tune.ntt3_mid = env_int("RONK_NTT3_MID", 1);
+  ctx->tune.ntt3_split = env_int("RONK_NTT3_SPLIT", 1);
+  ctx->tune.ntt3_split_min16 = env_int("RONK_NTT3_SPLIT_MIN16", 1);
   ctx->tune.ntt16_cluster_max_batch = env_int("RONK_NTT16_CLUSTER_MAX_BATCH", 2);
   ctx->tune.ntt3_ng1_tiles = env_int("RONK_NTT3_NG1_TILES", 6);
   ctx->tune.ntt3_min_batch16 = env_int("RONK_NTT3_MIN_BATCH16", 1);

@@ -209,7 +209,7 @@ static int launch_tile(ronk_ctx* ctx, const F& f, const NttTileArgs& A, u32 tile
 }
 
 // ---- transforms as passes of 256-point tiles (ntt3_kernel.cuh): n = 2^24 (three passes) and n = 2^16 (two) -------
-template <class F, int PASS, bool INV, int LOGN, bool BOUNDED, int NG>
+template <class F, int PASS, bool INV, int LOGN, bool BOUNDED, int NG, int LI = 0>
 static int launch3_ng(ronk_ctx* ctx, const F& f, const Ntt3Args& A, const char* name, bool dependent, unsigned tiles) {
   LaunchScope ls(ctx, name);
   if (dependent && ctx->tune.ntt3_pdl && !ctx->prof) {
@@ -222,22 +222,22 @@ static int launch3_ng(ronk_ctx* ctx, const F& f, const Ntt3Args& A, const char* 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RONK_CUDA(ctx, cudaLaunchKernelEx(&cfg, ntt3_kernel<F, PASS, INV, LOGN, BOUNDED, NG>, f, A));
+    RONK_CUDA(ctx, cudaLaunchKernelEx(&cfg, ntt3_kernel<F, PASS, INV, LOGN, BOUNDED, NG, LI>, f, A));
   } else {
-    ntt3_kernel<F, PASS, INV, LOGN, BOUNDED, NG><<<tiles, N3_THREADS * (2 / NG), 0, ctx->stream>>>(f, A);
+    ntt3_kernel<F, PASS, INV, LOGN, BOUNDED, NG, LI><<<tiles, N3_THREADS * (2 / NG), 0, ctx->stream>>>(f, A);
   }
   return RONK_OK;
 }
-template <class F, int PASS, bool INV, int LOGN, bool BOUNDED>
+template <class F, int PASS, bool INV, int LOGN, bool BOUNDED, int LI = 0>
 static int launch3(ronk_ctx* ctx, const F& f, const Ntt3Args& A, const char* name, bool dependent) {
   const unsigned tiles = A.batch * (LOGN >= 21 ? (1u << (LOGN - 12)) : LOGN == 20 ? 256u : 16u);
   // a grid that leaves most warp slots empty runs one radix-16 group per thread (256 threads per tile): a single
   // 2^16- or 2^20-point transform is a chain of dependent carry chains per warp, and twice the warps halve it
   if constexpr ((LOGN == 16 || LOGN == 20) && !BOUNDED) {
     if (tiles < (unsigned)ctx->tune.ntt3_ng1_tiles * (unsigned)ctx->sm_count)
-      return launch3_ng<F, PASS, INV, LOGN, BOUNDED, 1>(ctx, f, A, name, dependent, tiles);
+      return launch3_ng<F, PASS, INV, LOGN, BOUNDED, 1, LI>(ctx, f, A, name, dependent, tiles);
   }
-  return launch3_ng<F, PASS, INV, LOGN, BOUNDED, 2>(ctx, f, A, name, dependent, tiles);
+  return launch3_ng<F, PASS, INV, LOGN, BOUNDED, 2, LI>(ctx, f, A, name, dependent, tiles);
 }
 
 // pass C of the 2^20-point transform (ntt3c_kernel): one thread per (transform, k2)
@@ -259,6 +259,16 @@ static int launch3c(ronk_ctx* ctx, const F& f, const Ntt3Args& A, const char* na
   } else {
     ntt3c_kernel<F, INV><<<blocks, N3C_THREADS, 0, ctx->stream>>>(f, A);
   }
+  return RONK_OK;
+}
+
+// first pass of a split transform (ntt3p_kernel): radix 2^LI over the elements n' apart, twiddle, in place
+template <class F, bool INV, int LI>
+static int launch3p(ronk_ctx* ctx, const F& f, const Ntt3Args& A, u32 log_np, u32 log_lo, const char* name) {
+  const u64 threads = (u64)A.batch << (log_np - (4 - LI));
+  const unsigned blocks = (unsigned)((threads + N3C_THREADS - 1) / N3C_THREADS);
+  LaunchScope ls(ctx, name);
+  ntt3p_kernel<F, INV, LI><<<blocks, N3C_THREADS, 0, ctx->stream>>>(f, A, log_np, log_lo);
   return RONK_OK;
 }
 
@@ -345,9 +355,13 @@ static int run_ntt16_cluster(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64
 // data = NTT(src [zero-extended from src_len]) [⊙ mul], the first dst_len outputs stored.  Pass 1 src → workspace, pass 2
 // in place in the workspace (its input and output views coincide), pass 3 workspace → data: src is only read, data only
 // written by the last pass, so src == data (in place) and a short data buffer (dst_len words) are both fine.
-template <class F, bool INV, int LOGN, bool BOUNDED>
+// LI > 0: a SPLIT transform n = 2^LI·2^LOGN (2^17 … 2^19 over 2^16, 2^25 / 2^26 over 2^24): `outer` is the n-point plan (its
+// two-level tables feed the first pass), pl_c the 2^LOGN-point plan of the 2^LI·batch sub-transforms; ntt3p_kernel runs
+// first (src → data, in place when they coincide) and the last pass interleaves the sub-transforms' outputs.
+template <class F, bool INV, int LOGN, bool BOUNDED, int LI = 0>
 static int run_ntt3(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, const u64* src, const u64* mul, u32 batch,
-                    u64 src_len, u64 dst_len, u64 mul_mask = ~0ULL) {
+                    u64 src_len, u64 dst_len, u64 mul_mask = ~0ULL, const NttPlan* outer = nullptr) {
+  static_assert(LI == 0 || ((LOGN == 16 || LOGN == 24) && !BOUNDED), "split transforms: over 2^16 or 2^24, unbounded");
   NttPlan& pl = const_cast<NttPlan&>(pl_c);
   const int d = INV ? 1 : 0;
   const u64 n = (u64)1 << LOGN;
@@ -363,6 +377,20 @@ static int run_ntt3(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, c
       pl.t1[d] = nullptr;
     }
     RONK_TRY(check_launch(ctx, "ntt3_t1_kernel"));
+  }
+  if (LI > 0) {
+    if (!outer || !outer->tw_lo || !outer->tw2 || batch > (0x7FFFFFFFu >> (12 + LI))) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
+    Ntt3Args P = {};
+    P.src = src;
+    P.dst = data;
+    P.tw_lo = outer->tw_lo;
+    P.tw_hi = outer->tw2;
+    P.scale_tw = INV ? f.to_tw(h_powmod((u64)1 << LI, pl.p - 2, pl.p)) : 0;   // 2^-LI: the rest of n^-1 rides on the sub-transforms' tables
+    P.batch = batch;
+    RONK_TRY((launch3p<F, INV, LI>(ctx, f, P, (u32)LOGN, outer->log_n1, INV ? "intt3_split" : "ntt3_split")));
+    RONK_TRY(check_launch(ctx, "ntt3 split pass"));
+    src = data;
+    batch <<= LI;
   }
   if (batch > (0x7FFFFFFFu >> 12)) return set_err(ctx, RONK_EUNSUPPORTED, "batch too large");
   RONK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, ((size_t)batch << LOGN) * sizeof(u64)));
@@ -407,9 +435,23 @@ static int run_ntt3(ronk_ctx* ctx, const F& f, const NttPlan& pl_c, u64* data, c
     A.dst = data;
     A.mul_src = mul;
     A.flags = mul ? NTT_FLAG_MUL : 0;
-    RONK_TRY((launch3<F, 3, INV, LOGN, BOUNDED>(ctx, f, A, INV ? "intt3_pass3" : "ntt3_pass3", true)));
+    RONK_TRY((launch3<F, 3, INV, LOGN, BOUNDED, LI>(ctx, f, A, INV ? "intt3_pass3" : "ntt3_pass3", true)));
     return check_launch(ctx, "ntt3 pass 3");
   }
+}
+
+// the plan of another size for the same (p, g), built on demand (std::map: references to other plans stay valid)
+template <class F>
+static int sub_plan(ronk_ctx* ctx, const F& f, u64 p, u64 g, u32 log_n, const NttPlan** out) {
+  auto key = std::make_tuple((uint64_t)p, (uint64_t)g, (uint32_t)log_n);
+  auto it = ctx->plans.find(key);
+  if (it == ctx->plans.end()) {
+    NttPlan pl;
+    RONK_TRY(build_plan(ctx, f, p, g, log_n, &pl));
+    it = ctx->plans.emplace(key, pl).first;
+  }
+  *out = &it->second;
+  return RONK_OK;
 }
 
 // src == nullptr: in place.  Otherwise (batch == 1) the transform reads src[0, src_len) zero-extended to n
@@ -441,6 +483,20 @@ static int run_ntt(ronk_ctx* ctx, const F& f, const NttPlan& pl, u64* data, cons
       // 2^16: worth it once the grid fills the GPU (16 tiles per transform); single transforms stay launch-bound
       if (log_n == 24 && !bounded) return run_ntt3<F, INV, 24, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
       if (log_n == 24 && batch == 1) return run_ntt3<F, INV, 24, true>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
+      if (!bounded && ctx->tune.ntt3_split && ((log_n >= 17 && log_n <= 19 && (batch << (log_n - 16)) >= (u32)ctx->tune.ntt3_split_min16) ||
+                                               log_n == 25 || log_n == 26)) {
+        // split transforms: a radix-2/4/8 register pass, then 2^16- or 2^24-point tile transforms whose last pass interleaves
+        const u32 lsub = log_n >= 25 ? 24u : 16u;
+        const NttPlan* sub = nullptr;
+        RONK_TRY((sub_plan<F>(ctx, f, pl.p, pl.g, lsub, &sub)));
+        switch (log_n) {
+          case 17: return run_ntt3<F, INV, 16, false, 1>(ctx, f, *sub, data, src, mul, batch, src_len, dst_len, mul_mask, &pl);
+          case 18: return run_ntt3<F, INV, 16, false, 2>(ctx, f, *sub, data, src, mul, batch, src_len, dst_len, mul_mask, &pl);
+          case 19: return run_ntt3<F, INV, 16, false, 3>(ctx, f, *sub, data, src, mul, batch, src_len, dst_len, mul_mask, &pl);
+          case 25: return run_ntt3<F, INV, 24, false, 1>(ctx, f, *sub, data, src, mul, batch, src_len, dst_len, mul_mask, &pl);
+          default: return run_ntt3<F, INV, 24, false, 2>(ctx, f, *sub, data, src, mul, batch, src_len, dst_len, mul_mask, &pl);
+        }
+      }
       if (log_n >= 21 && log_n <= 23 && !bounded && ctx->tune.ntt3_mid) {   // 2^21 … 2^23: first pass of 32 / 64 / 128 points, then as 2^24
         if (log_n == 21) return run_ntt3<F, INV, 21, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);
         if (log_n == 22) return run_ntt3<F, INV, 22, false>(ctx, f, pl, data, src, mul, batch, src_len, dst_len, mul_mask);

@@ -82,6 +82,7 @@ namespace ronk {
 constexpr u32 N3_THREADS = 128;   // NG = 2 groups per thread (full grids); NG = 1: 256 threads, one group each — twice
                                   // the warps per tile for grids that do not fill the GPU (single 2^16 / 2^20 transforms)
 constexpr u32 N3_TILE_WORDS = 16 * 272;  // 4352 words = 34 816 B
+constexpr u32 N3C_THREADS = 128;         // the register-only passes (ntt3c_kernel, ntt3p_kernel)
 RONK_HD constexpr u32 n3_word(u32 d1, u32 d0, u32 c) { return 272u * d1 + 17u * d0 + c; }
 RONK_HD constexpr u32 n3_br4(int j) { return (u32)(((j & 1) << 3) | ((j & 2) << 1) | ((j & 4) >> 1) | ((j & 8) >> 3)); }
 
@@ -108,6 +109,7 @@ struct Ntt3Args {
                        // every transform of the batch (the twiddle column of the distributed transform)
   u64 src_len;         // BOUNDED kernels (batch = 1): the first pass reads src[0, src_len) zero-extended,
   u64 dst_len;         //                               the last pass stores dst[0, dst_len) only
+  u64 scale_tw;        // ntt3p_kernel, inverse only: R^-1 in twiddle form (the sub-transforms' tables carry n'^-1, not n^-1)
   u32 batch;
   u32 flags;           // NTT_FLAG_MUL
 };
@@ -117,8 +119,12 @@ struct Ntt3Args {
 // PASS 3:    group g ↔ (col = g >> 4, d0 = g & 15): element q is i = 16 q + d0 of column col (i is the contiguous axis).
 // First pass of 2^21 … 2^23 (LR0 = log2 R0 < 4, PASS 1 only): register q = u·R0 + d1 is row 16·d1 + d0 of sub-transform u,
 // whose sixteen columns start 16·u after this thread's; radix_network<LR0> runs the 16 / R0 networks side by side.
-template <class F, int PASS, bool INV, bool BOUNDED = false, int NG = 2, int LR0 = 4>
-RONK_DEV void n3_round0(const F& f, u64* smem, const Ntt3Args& A, u64 tile_base, u64 row_stride, u64 col_stride, u32 tid) {
+// Last pass of a SPLIT transform (n = 2^LI · n', LI > 0, PASS 3 only): the sixteen columns of the tile are 16 / 2^LI
+// consecutive k1' of EACH of the 2^LI sub-transforms (column c ↔ sub-transform c mod 2^LI, sub_stride = n' words apart),
+// so that the stores of round 1 — X[sub + 2^LI·k'] — are again sixteen contiguous words.
+template <class F, int PASS, bool INV, bool BOUNDED = false, int NG = 2, int LR0 = 4, int LI = 0>
+RONK_DEV void n3_round0(const F& f, u64* smem, const Ntt3Args& A, u64 tile_base, u64 row_stride, u64 col_stride, u32 tid,
+                        u64 sub_stride = 0) {
   constexpr u32 R0 = 1u << LR0;
 #if RONK_NTT3_UNROLL_GROUPS == 1
 #pragma unroll 1
@@ -128,7 +134,8 @@ RONK_DEV void n3_round0(const F& f, u64* smem, const Ntt3Args& A, u64 tile_base,
   for (int h = 0; h < NG; h++) {
     const u32 g = tid + (u32)h * N3_THREADS;
     const u32 d0 = (PASS == 3) ? (g & 15u) : (g >> 4), c = (PASS == 3) ? (g >> 4) : (g & 15u);
-    const u64* p = A.src + tile_base + (u64)d0 * row_stride + (u64)c * col_stride;
+    const u64* p = A.src + tile_base + (u64)d0 * row_stride +
+                   ((PASS == 3 && LI > 0) ? (u64)(c & ((1u << LI) - 1u)) * sub_stride + (u64)(c >> LI) * col_stride : (u64)c * col_stride);
 #if (RONK_NTT3_EARLY_TW & 2) && defined(__CUDA_ARCH__)
     if (NG == 2 && h == 0 && !BOUNDED) {   // the second group's sixteen rows on their way (L2) while the first is computed
       const u32 g1 = g + N3_THREADS;
@@ -326,8 +333,33 @@ RONK_DEV void n3_round1_cluster(const F& f, const u64* smem, const Ntt3Args& A, 
 // LOGN = 16 (n = 256·256, BASELINE config 5): the same two kernels without pass 1 — 16 tiles per transform:
 //   pass 2: tile = s: rows j1 (stride 256), columns j2 = 16 s + c, twiddle ω_n^(k1·j2) = the [k1][j2] table
 //   pass 3: tile = t: input column col ↔ k1 = 16 t + col (stride 256), i = j2 contiguous; output X[k1 + 256 k2]
-template <int PASS, int LOGN>
+template <int PASS, int LOGN, int LI = 0>
 RONK_DEV void n3_tile_geometry(u32 tile, u64* in_base, u64* in_row, u64* in_col, u64* out_base, u64* out_row, u32* m_base) {
+  if (PASS == 3 && LI > 0) {
+    // last pass of a split transform n = 2^LI·n', n' = 2^LOGN (16 or >= 21): a tile serves 16 >> LI values of k1' of all
+    // 2^LI sub-transforms of one n-point transform gb; out view: X[sub + 2^LI·(k1' + R' k2 [+ 256 R' k3])]
+    constexpr int L = LOGN >= 21 ? LOGN : 24;
+    if (LOGN == 16) {
+      const u64 gb = tile >> (4 + LI);
+      const u32 tt = tile & ((16u << LI) - 1u);
+      *in_base = (gb << (16 + LI)) + ((u64)((16u >> LI) * tt) << 8);
+      *in_row = 1;
+      *in_col = 256;
+      *out_base = (gb << (16 + LI)) + 16u * tt;
+      *out_row = (u64)256 << LI;
+    } else {
+      const u64 gb = tile >> (L - 12 + LI);
+      const u32 t = tile & ((1u << (L - 12 + LI)) - 1u);
+      const u32 hi = t >> (L - 20 + LI), lo = t & ((1u << (L - 20 + LI)) - 1u);   // hi = k2, lo = tt
+      *in_base = (gb << (L + LI)) + ((u64)((16u >> LI) * lo) << 16) + ((u64)hi << 8);
+      *in_row = 1;
+      *in_col = 65536;
+      *out_base = (gb << (L + LI)) + ((u64)hi << (L - 16 + LI)) + 16u * lo;
+      *out_row = (u64)1 << (L - 8 + LI);
+    }
+    *m_base = 0;
+    return;
+  }
   if (LOGN == 16) {
     const u64 b = tile >> 4;
     const u32 lo = tile & 15u;
@@ -393,6 +425,39 @@ RONK_DEV void n3_tile_geometry(u32 tile, u64* in_base, u64* in_row, u64* in_col,
   }
 }
 
+// First pass of a split transform n = R·n', R = 2^LI <= 8 (2^17 … 2^19 = R·2^16, 2^25 / 2^26 = R·2^24): for every column
+// m < n' a radix-R network over the R elements n' apart, times ω_n^(±k1·m) (w = ω_n^(±m) from the two-level tables, its
+// powers by repeated multiplication), in place.  A thread takes 16 / R columns, n' / (16 / R) apart: sixteen registers,
+// every access coalesced.  Sub-transform k1 = bitrev(register index) is the contiguous block [k1·n', (k1+1)·n').
+template <class F, bool INV, int LI>
+RONK_DEV void n3p_columns(const F& f, const Ntt3Args& A, u64 base, u64 mm, u32 log_np, u32 log_lo) {
+  constexpr u32 R = 1u << LI, CT = 16u >> LI;
+  const u64 np = (u64)1 << log_np, cstep = np / CT;
+  const u64* p = A.src + base + mm;
+  u64 x[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) x[q] = p[(u64)((u32)q & (R - 1u)) * np + (u64)((u32)q >> LI) * cstep];
+  radix_network<LI, INV>(f, x);
+  u64* o = A.dst + base + mm;
+  const u32 nmask = (u32)((np << LI) - 1u);
+#pragma unroll
+  for (u32 u = 0; u < CT; u++) {
+    u32 ex = (u32)(mm + (u64)u * cstep);          // m < n' <= 2^24
+    if (INV) ex = (0u - ex) & nmask;
+    const u64 w1 = f.mul_tw(ld_tw(A.tw_lo + (ex & ((1u << log_lo) - 1u))), ld_tw(A.tw_hi + (ex >> log_lo)));
+    u64 wk[R];                                     // wk[k] = ω_n^(±k·m) [· R^-1 for the inverse] in twiddle form, k >= 1
+    wk[1] = INV ? f.mul_tw(w1, A.scale_tw) : w1;
+#pragma unroll
+    for (u32 k = 2; k < R; k++) wk[k] = f.mul_tw(wk[k - 1], w1);
+#pragma unroll
+    for (u32 j = 0; j < R; j++) {
+      const u32 k1 = n3_brn(j, LI);
+      const u64 v = x[u * R + j];
+      o[(u64)k1 * np + (u64)u * cstep] = k1 ? f.mul_tw(v, wk[k1]) : (INV ? f.mul_tw(v, A.scale_tw) : v);
+    }
+  }
+}
+
 // pass C body for one (transform b, k2): register q of the DIF network holds output k1 = bitrev4(q)
 template <class F, bool INV>
 RONK_DEV void n3c_point(const F& f, const Ntt3Args& A, u64 b, u64 k2) {
@@ -413,19 +478,19 @@ RONK_DEV void n3c_point(const F& f, const Ntt3Args& A, u64 b, u64 k2) {
 }
 
 #if defined(__CUDACC__)
-template <class F, int PASS, bool INV, int LOGN, bool BOUNDED, int NG = 2>
+template <class F, int PASS, bool INV, int LOGN, bool BOUNDED, int NG = 2, int LI = 0>
 __global__ void __launch_bounds__(N3_THREADS * (2 / NG), RONK_NTT3_MINB / (2 / NG)) ntt3_kernel(const F f, const Ntt3Args A) {
   __shared__ u64 smem[N3_TILE_WORDS];
   const u32 tid = threadIdx.x;
   u64 in_base, in_row, in_col, out_base, out_row;
   u32 m_base;
-  n3_tile_geometry<PASS, LOGN>(blockIdx.x, &in_base, &in_row, &in_col, &out_base, &out_row, &m_base);
+  n3_tile_geometry<PASS, LOGN, LI>(blockIdx.x, &in_base, &in_row, &in_col, &out_base, &out_row, &m_base);
   // programmatic dependent launch: a pass may be scheduled while its predecessor's last wave is still running; it must
   // not touch the predecessor's output before griddepcontrol.wait (no-ops without the launch attribute)
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  n3_round0<F, PASS, INV, BOUNDED && PASS == (LOGN >= 21 ? 1 : 2), NG, (PASS == 1 && LOGN >= 21) ? n3_log_r0(LOGN) : 4>(
-      f, smem, A, in_base, in_row, in_col, tid);  // src_len: first pass only
+  n3_round0<F, PASS, INV, BOUNDED && PASS == (LOGN >= 21 ? 1 : 2), NG, (PASS == 1 && LOGN >= 21) ? n3_log_r0(LOGN) : 4, LI>(
+      f, smem, A, in_base, in_row, in_col, tid, (u64)1 << LOGN);  // src_len: first pass only
   __syncthreads();
   n3_round1<F, PASS, INV, BOUNDED, LOGN, NG>(f, smem, A, out_base, out_row, m_base, tid);
 }
@@ -465,9 +530,19 @@ __global__ void __launch_bounds__(2 * N3_THREADS, 3) ntt16c_kernel(const F f, co
   n3_round1<F, 3, INV, false, 16, 1>(f, tile, A, out_base, out_row, m_base, tid);
 }
 
+template <class F, bool INV, int LI>
+__global__ void __launch_bounds__(N3C_THREADS) ntt3p_kernel(const F f, const Ntt3Args A, u32 log_np, u32 log_lo) {
+  const u64 i = (u64)blockIdx.x * N3C_THREADS + threadIdx.x;   // < batch · n' / (16 / R)
+  const u32 log_ct = 4 - LI, log_per = log_np - log_ct;
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (i >= ((u64)A.batch << log_per)) return;
+  const u64 b = i >> log_per, mm = i & (((u64)1 << log_per) - 1);
+  n3p_columns<F, INV, LI>(f, A, b << (log_np + LI), mm, log_np, log_lo);
+}
+
 // pass C of the 2^20-point transform: one thread per (transform, k2) — sixteen contiguous words in, a radix-16 network in
 // registers (no twiddles: ω_16 is a power of two), sixteen stores at stride 65536, coalesced across the warp.
-constexpr u32 N3C_THREADS = 128;
 template <class F, bool INV>
 __global__ void __launch_bounds__(N3C_THREADS) ntt3c_kernel(const F f, const Ntt3Args A) {
   const u64 i = (u64)blockIdx.x * N3C_THREADS + threadIdx.x;   // < batch · 65536

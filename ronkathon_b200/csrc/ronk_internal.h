@@ -53,6 +53,9 @@ struct ronk_tune {
                                     // path wins from batch 4 on (8 transforms: 10.9 vs 15.6 µs)
   int ntt3_ng1_tiles = 6;   // RONK_NTT3_NG1_TILES: grids below this many tiles per SM run one group per thread (256 threads per tile);
                             // measured (profiles/r02r_switches.txt): 6 vs 3 — two 2^20-point transforms 0.0453 vs 0.0488 ms, rest equal
+  int ntt3_split = 1;       // RONK_NTT3_SPLIT: 2^17 … 2^19 and 2^25 / 2^26 as a radix-2/4/8 register pass + interleaved 2^16- / 2^24-point tile transforms
+  int ntt3_split_min16 = 1; // RONK_NTT3_SPLIT_MIN16: … for 2^17 … 2^19 only from this many 2^16-point sub-transforms on.  Measured
+                            // (profiles/r03e_ab.txt): even ONE transform gains (2^18: 14.6 vs 16.6 µs, 2^19: 16.5 vs 22.7 µs), so 1
   int ntt3_mid = 1;         // RONK_NTT3_MID: 2^21 … 2^23-point transforms through the 256-point-tile kernels (first pass of 32 / 64 / 128 points)
   int ntt3_20 = 1;          // RONK_NTT3_20: 2^20-point transforms as 16 interleaved 2^16-point tile transforms + one radix-16 pass
   int ntt3_t1 = 1;          // RONK_NTT3_T1: pass-1 twiddles ω_n^(k1·m) of the 2^24-point transform from a 128 MiB table per direction

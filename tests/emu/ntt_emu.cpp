@@ -200,27 +200,42 @@ int run(const F& f, u64 p, u64 g, bool fast_gl, u64* data, const u64* mul, u32 l
 unsigned long long g_ntt3_mul_mask = ~0ULL;  // n - 1: the multiplier is ONE n-word table shared by the whole batch
 int g_ntt3_ng1 = 0;  // 1: the 256-thread (one group per thread) flavour of the 2^16 / 2^20 tile passes
 // The three-pass 2^24 transform (ntt3_kernel.cuh), phase by phase like ntt3_kernel; tables as run_ntt3() builds them.
-template <class F, int PASS, bool INV, int LOGN, bool BOUNDED = false>
+template <class F, int PASS, bool INV, int LOGN, bool BOUNDED = false, int LI = 0>
 void run_pass3(const F& f, const Ntt3Args& A) {
   std::vector<u64> smem(N3_TILE_WORDS);
   for (u32 tile = 0; tile < A.batch * (LOGN >= 21 ? (1u << (LOGN - 12)) : LOGN == 20 ? 256u : 16u); tile++) {
     u64 in_base, in_row, in_col, out_base, out_row;
     u32 m_base;
-    n3_tile_geometry<PASS, LOGN>(tile, &in_base, &in_row, &in_col, &out_base, &out_row, &m_base);
-    if (g_ntt3_ng1 && LOGN != 24) {   // one group per thread, 256 threads per tile (grids that do not fill the GPU)
+    n3_tile_geometry<PASS, LOGN, LI>(tile, &in_base, &in_row, &in_col, &out_base, &out_row, &m_base);
+    if (g_ntt3_ng1 && LOGN != 24 && LI == 0) {   // one group per thread, 256 threads per tile (grids that do not fill the GPU)
       for (u32 t = 0; t < 2 * N3_THREADS; t++) n3_round0<F, PASS, INV, false, 1>(f, smem.data(), A, in_base, in_row, in_col, t);
       for (u32 t = 0; t < 2 * N3_THREADS; t++) n3_round1<F, PASS, INV, false, LOGN, 1>(f, smem.data(), A, out_base, out_row, m_base, t);
       continue;
     }
     for (u32 t = 0; t < N3_THREADS; t++)
-      n3_round0<F, PASS, INV, BOUNDED && PASS == (LOGN >= 21 ? 1 : 2), 2, (PASS == 1 && LOGN >= 21) ? n3_log_r0(LOGN) : 4>(f, smem.data(), A, in_base, in_row, in_col, t);
+      n3_round0<F, PASS, INV, BOUNDED && PASS == (LOGN >= 21 ? 1 : 2), 2, (PASS == 1 && LOGN >= 21) ? n3_log_r0(LOGN) : 4, LI>(
+          f, smem.data(), A, in_base, in_row, in_col, t, (u64)1 << LOGN);
     for (u32 t = 0; t < N3_THREADS; t++) n3_round1<F, PASS, INV, BOUNDED, LOGN>(f, smem.data(), A, out_base, out_row, m_base, t);
   }
 }
 int g_ntt3_t1 = 0;  // 1: pass-1 twiddles from the n-word table
-template <class F, bool INV, int LOGN, bool BOUNDED = false>
+template <class F, bool INV, int LOGN, bool BOUNDED = false, int LI = 0>
 int run3(const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 batch, const u64* src = nullptr, u64 src_len = ~0ULL,
          u64 dst_len = ~0ULL) {
+  if (LI > 0) {   // split transform n = 2^LI·2^LOGN: the register first pass with the n-point plan's two-level tables, in place
+    const u32 log_n = LOGN + LI, lo = (log_n + 1) / 2;
+    const u64 nn = (u64)1 << log_n;
+    const u64 wn = h_powmod(g, (p - 1) / nn, p);
+    auto o_lo = table(f, wn, 1, 1u << lo);
+    auto o_hi = table(f, h_powmod(wn, (u64)1 << lo, p), 1, 1u << (log_n - lo));
+    Ntt3Args P = {};
+    P.src = data; P.dst = data; P.tw_lo = o_lo.data(); P.tw_hi = o_hi.data(); P.batch = batch;
+    P.scale_tw = INV ? f.to_tw(h_powmod((u64)1 << LI, p - 2, p)) : 0;
+    const u32 log_per = LOGN - (4 - LI);
+    for (u64 i = 0; i < ((u64)batch << log_per); i++)
+      n3p_columns<F, INV, LI>(f, P, (i >> log_per) << log_n, i & (((u64)1 << log_per) - 1), LOGN, lo);
+    batch <<= LI;
+  }
   const u64 n = (u64)1 << LOGN;
   u64 w = h_powmod(g, (p - 1) / n, p);
   const u64 wf = w;
@@ -278,7 +293,7 @@ int run3(const F& f, u64 p, u64 g, u64* data, const u64* mul, u32 batch, const u
   }
   run_pass3<F, 2, INV, LOGN, BOUNDED && LOGN == 16>(f, A);
   A.src = ws.data(); A.dst = data; A.mul_src = mul; A.flags = mul ? NTT_FLAG_MUL : 0;
-  run_pass3<F, 3, INV, LOGN, BOUNDED>(f, A);
+  run_pass3<F, 3, INV, LOGN, BOUNDED, LI>(f, A);
   return 0;
 }
 
@@ -405,6 +420,15 @@ int emu_ntt3(uint64_t* data, const uint64_t* mul, uint32_t log_n, uint32_t batch
     return inverse ? run3<GoldilocksField, true, 22>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 22>(f, GL_P, 7, data, mul, batch);
   if (log_n == 23)
     return inverse ? run3<GoldilocksField, true, 23>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 23>(f, GL_P, 7, data, mul, batch);
+  // split transforms: 2^17 … 2^19 over 2^16, 2^25 over 2^24 (2^26 runs the same code with LI = 2: too slow for the CPU tier)
+  if (log_n == 17)
+    return inverse ? run3<GoldilocksField, true, 16, false, 1>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 16, false, 1>(f, GL_P, 7, data, mul, batch);
+  if (log_n == 18)
+    return inverse ? run3<GoldilocksField, true, 16, false, 2>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 16, false, 2>(f, GL_P, 7, data, mul, batch);
+  if (log_n == 19)
+    return inverse ? run3<GoldilocksField, true, 16, false, 3>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 16, false, 3>(f, GL_P, 7, data, mul, batch);
+  if (log_n == 25)
+    return inverse ? run3<GoldilocksField, true, 24, false, 1>(f, GL_P, 7, data, mul, batch) : run3<GoldilocksField, false, 24, false, 1>(f, GL_P, 7, data, mul, batch);
   return 1;
 }
 // forward transforms ⊙ ONE n-word multiplier shared by the batch (the twiddle column of the distributed transform)

@@ -479,3 +479,38 @@ def test_mid_sizes_through_the_tile_kernels(log_n, batch):
         c1.sync()
         assert np.array_equal(host(z), a), env
         c1.close()
+
+
+@pytest.mark.parametrize("log_n,batch", [(17, 32), (18, 17), (19, 8), (25, 1)])
+def test_split_transforms_match_oracle_and_the_two_pass_path(log_n, batch):
+    """n = R·2^16 (batches of 2^17 … 2^19) and n = 2·2^24: a radix-R register pass, then R tile transforms whose last
+    pass interleaves their outputs.  Sampled transforms against the oracle, fused multiply against a separate
+    point-wise product, inverse round trip, and bit-for-bit agreement with RONK_NTT3_SPLIT=0."""
+    import os
+    import torch
+    from ronkathon_b200 import Context, ops
+    c0 = ctx()
+    n = 1 << log_n
+    a = ops.splitmix_fill(c0, n * batch, 700 + log_n, GL)
+    m = ops.splitmix_fill(c0, n * batch, 710 + log_n, GL)
+    ah = host(a)
+    x = a.clone()
+    ops.ntt_(c0, x, log_n, batch)
+    X = host(x)
+    for b in sorted({0, batch // 2, batch - 1}):
+        assert np.array_equal(X[b * n:(b + 1) * n], oracle.ntt_fast(GL, ah[b * n:(b + 1) * n])), b
+    y = a.clone()
+    ops.ntt_mul_(c0, y, m, log_n, batch)
+    assert np.array_equal(host(y), oracle.vec_mul(GL, X, host(m)))
+    ops.ntt_(c0, x, log_n, batch, inverse=True)
+    assert np.array_equal(host(x), ah)
+    os.environ["RONK_NTT3_SPLIT"] = "0"
+    try:
+        c1 = Context(0, torch.cuda.current_stream().cuda_stream)
+    finally:
+        os.environ.pop("RONK_NTT3_SPLIT")
+    z = a.clone()
+    ops.ntt_(c1, z, log_n, batch)
+    c1.sync()
+    assert np.array_equal(host(z), X)
+    c1.close()

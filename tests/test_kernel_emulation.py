@@ -336,6 +336,25 @@ def test_2_16_cluster_formulation_in_place(emu):
     assert np.array_equal(X, a)
 
 
+@pytest.mark.parametrize("log_n,batch", [(17, 2), (18, 1), (19, 2), (25, 1)])
+def test_split_transforms_register_first_pass_and_interleaving_last_pass(emu, log_n, batch):
+    """n = R·2^16 (2^17 … 2^19) and n = 2·2^24: a radix-R register pass with the twiddles ω_n^(k1·m), then R tile transforms
+    whose last pass writes X[k1 + R·k'] as contiguous 16-word runs: forward against the oracle, fused multiply, inverse."""
+    n = 1 << log_n
+    a = oracle.splitmix(GL, 40 + log_n, n * batch)
+    m = oracle.splitmix(GL, 50 + log_n, n * batch)
+    X = a.copy()
+    assert emu.emu_ntt3(_ptr(X), None, log_n, batch, 0, 1) == 0
+    for b in range(batch):
+        assert np.array_equal(X[b * n:(b + 1) * n], oracle.ntt_fast(GL, a[b * n:(b + 1) * n])), b
+    if log_n < 25:
+        Y = a.copy()
+        assert emu.emu_ntt3(_ptr(Y), _ptr(m), log_n, batch, 0, 1) == 0
+        assert np.array_equal(Y, oracle.vec_mul(GL, X, m))
+    assert emu.emu_ntt3(_ptr(X), None, log_n, batch, 1, 1) == 0
+    assert np.array_equal(X, a)
+
+
 @pytest.mark.parametrize("log_n,batch", [(16, 3), (20, 2), (21, 2)])
 def test_shared_multiplier_of_a_batch(emu, log_n, batch):
     """The fused point-wise multiply with ONE n-word multiplier for the whole batch (mask n - 1 on the multiplier
